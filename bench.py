@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py -- Biot-Savart pair interactions per second on B200 (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c1|c5|c3grad]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one evaluation of the hot path over one synthetic particle set: the
+points-on-points direct sum that Convection::find_vels runs per Runge-Kutta substep
+(reference src/Convection.h:172-223 -> src/Influence.h:347-361).
+
+Default workload (N=1): BASELINE.json configs[2], "C3": 1M-particle Gaussian vortex blob,
+Rosenhead-Moore core, per-particle radii, velocity on blob targets (kernelu_0v_0b): 1e12 pairs/step.
+At N>1 GPUs the particle count follows the weak-scaling recipe of SURVEY 8d/C5 (N_P = N_1 sqrt(P),
+constant pairs per GPU); targets are sharded in contiguous blocks and every rank's packed source
+block is all-gathered once per step over NVLink (o2d_points_on_points_sharded).
+
+Printed keys (one JSON line from rank 0):
+  value     whole-job interactions/s, inputs resident in HBM, CUDA-event time, max over ranks
+  e2e       same metric through the C ABI with HOST (pinned) buffers: H2D of sources/targets/outputs and
+            D2H of the velocities inside the timed region
+  roofline  dominant pair-sum kernel: reference-counted flops per pair x pairs / kernel time (events inside
+            the library, on the launching stream) against the FP32 non-tensor peak
+  cpu_baseline  the reference's own OpenMP loop (oracle/_ref) on this box's host cores, bounded target sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from omega2d_b200 import sharding, workloads as W  # noqa: E402
+
+METRIC = "biot_savart_pair_interactions_per_sec"
+UNIT = "interactions/s"
+
+WORKLOADS = {
+    # name: (generator, core, results, description)
+    "c3": dict(n=1_000_000, core="rm", results=1, blob=True,
+               desc="C3: synthetic 1M-particle Gaussian vortex blob, Rosenhead-Moore core, per-particle radii, "
+                    "velocity on blob targets (kernelu_0v_0b)"),
+    "c3grad": dict(n=1_000_000, core="rm", results=2, blob=True,
+                   desc="C3: 1M-particle Gaussian vortex blob, Rosenhead-Moore core, velocity + gradient (kernelug_0v_0b)"),
+    "c1": dict(n=20_000, core="v2", results=1, blob=True,
+               desc="C1: speedtest20kx10 restated, 20k blobs, Vatistas-2 core, velocity"),
+    "c5": dict(n=16_777_216, core="wl", results=1, blob=True,
+               desc="C5: 16M-particle Gaussian blob, Winckelmans-Leonard core, velocity"),
+    "v2": dict(n=1_000_000, core="v2", results=1, blob=True,
+               desc="1M-particle Gaussian vortex blob, Vatistas-2 core (reference default), velocity"),
+}
+
+
+def make_particles(name: str, n: int):
+    if name == "c1":
+        return W.c1_speedtest(n)
+    return W.gaussian_blob(n, seed=2024, vary_radius=True)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=0, help="override the particle count at 1 GPU")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of one cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU side: the reference's own loop (oracle/_ref) or, if that was never built, the C port
+# ---------------------------------------------------------------------------------------------
+def cpu_checker(core: str):
+    import oracle
+    if oracle.have_ref():
+        r = oracle.ref(core)
+        return "reference", (lambda res, *a: r.points_on_points(res, *a))
+    p = oracle.port()
+    return "port", (lambda res, *a: p.points_on_points(core, res, *a))
+
+
+def cpu_sample(wl, parts, seconds: float):
+    """Time the CPU path on a strided target subset against ALL sources (onbody's ntskip
+    method, reference extern/onbody/src/main2dvort.cpp:116-133), sized for ~`seconds`."""
+    kind, fn = cpu_checker(wl["core"])
+    sx, sy, ss, sr = parts
+    n = sx.size
+    res = 1 if wl["results"] == 2 else wl["results"]   # the reference has no velandgrad loop
+
+    def run(count):
+        sub = W.strided_subset(n, count)
+        t0 = time.perf_counter()
+        out = fn(res, sx, sy, ss, sr, sx[sub], sy[sub], sr[sub] if wl["blob"] else None)
+        return time.perf_counter() - t0, sub, out
+
+    cal = min(n, max(64, int(2e8 // max(n, 1))))
+    dt, _, _ = run(cal)                       # warm-up + calibration
+    rate = cal * n / max(dt, 1e-6)
+    count = int(min(n, max(cal, seconds * rate / n)))
+    return kind, run, count
+
+
+def run_reference_arm(args, wl, n):
+    """--impl reference: the reference's OpenMP direct sum on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    parts = make_particles(args.workload, n)
+    kind, run, count = cpu_sample(wl, parts, args.cpu_seconds)
+    for _ in range(max(0, args.warmup - 1)):   # calibration already ran the path once
+        run(min(count, 256))
+    times = []
+    for _ in range(args.steps):
+        dt, _, _ = run(count)
+        times.append(dt)
+    total = sum(times)
+    value = args.steps * count * n / total
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32 pair terms, f64 accumulation",
+        "data": "synthetic",
+        "config": {"workload": wl["desc"], "particles": n, "core": wl["core"],
+                   "sample": f"{count} strided targets x {n} sources per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{count} strided targets x all {n} sources per step, OpenMP on all host cores, USE_VC off"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.path = tempfile.mktemp(prefix="o2d_clocks_", suffix=".csv")
+        self.proc = None
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(device_index)],
+                stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for ln in open(self.path):
+                p = [x.strip() for x in ln.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1])); mx.append(float(p[2])); pw.append(float(p[3]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, p[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            # keep samples taken under load (top half of power draw)
+            thr = np.median(pw)
+            load = [s for s, w in zip(sm, pw) if w >= thr]
+            out.update(sm_mhz=float(np.median(load)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=float(max(pw)))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args, wl, n1):
+    import torch
+    import torch.distributed as dist
+    import omega2d_b200 as o2d
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; omega2d_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = n1 if (world == 1 or args.scaling == "strong") else sharding.weak_scaling_count(n1, world)
+    lo, hi = sharding.block_range(n, world, rank)
+    nblock = sharding.block_size(n, world)
+    nloc = hi - lo
+    parts = make_particles(args.workload, n)          # every rank generates the same seeded set
+    sx, sy, ss, sr = parts
+    core, results = wl["core"], wl["results"]
+    nout = {1: 2, 2: 6, 4: 3, 5: 3}[results]
+
+    ctx = o2d.Context(local_rank)
+    if world > 1:
+        uid = [o2d.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(world, rank, uid[0])
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    info = ctx.device_info()
+
+    # ---- device-resident inputs (this rank's block) --------------------------------------------
+    d = [torch.from_numpy(np.ascontiguousarray(a[lo:hi])).to(dev) for a in (sx, sy, ss, sr)]
+    outs = [torch.zeros(max(nloc, 1), device=dev) for _ in range(nout)]
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)   # > 126 MB L2
+
+    def step_device():
+        tq = outs[2] if nout == 3 else None
+        g = outs[2:6] if nout == 6 else [None] * 4
+        tr = d[3] if wl["blob"] else None
+        if world == 1:
+            ctx.points_on_points(core, results, o2d.MEM_DEVICE, nloc, d[0], d[1], d[2], d[3],
+                                 nloc, d[0], d[1], tr, outs[0], outs[1], tq, *g)
+        else:
+            ctx.points_on_points_sharded(core, results, o2d.MEM_DEVICE, nloc, nblock, d[0], d[1], d[2], d[3],
+                                         nloc, d[0], d[1], tr, outs[0], outs[1], tq, *g)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        for o in outs:
+            o.zero_()
+        step_device()
+    barrier()
+
+    # ---- timed region: exactly K steps, CUDA events on the launching stream -----------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ctx.reset_counters()
+    ctx.enable_timing(True)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(float(k))                 # evict L2 between timed iterations (outside the event pair)
+        for o in outs:
+            o.zero_()
+        ev[k][0].record(stream)
+        step_device()
+        ev[k][1].record(stream)
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if sampler else None
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    cnt = ctx.counters()
+    ctx.enable_timing(False)
+    t = torch.tensor([ms, cnt["pair_ms"]], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, pair_ms_max = float(t[0]), float(t[1])
+    pairs_per_step = float(n) * float(n)
+    value = args.steps * pairs_per_step / (ms_max * 1e-3)
+
+    # ---- result check on a few targets (oracle as checker only) --------------------------------------
+    u = outs[0][:nloc].cpu().numpy(); v = outs[1][:nloc].cpu().numpy()
+
+    # ---- e2e: HOST pinned buffers through the C ABI, H2D + D2H inside the timed region ------------------
+    e2e = None
+    if not args.no_e2e:
+        h = [torch.from_numpy(np.ascontiguousarray(a[lo:hi])).pin_memory() for a in (sx, sy, ss, sr)]
+        houts = [torch.zeros(max(nloc, 1)).pin_memory() for _ in range(nout)]
+
+        def step_host():
+            tq = houts[2] if nout == 3 else None
+            g = houts[2:6] if nout == 6 else [None] * 4
+            tr = h[3] if wl["blob"] else None
+            if world == 1:
+                ctx.points_on_points(core, results, o2d.MEM_HOST, nloc, h[0], h[1], h[2], h[3],
+                                     nloc, h[0], h[1], tr, houts[0], houts[1], tq, *g)
+            else:
+                ctx.points_on_points_sharded(core, results, o2d.MEM_HOST, nloc, nblock, h[0], h[1], h[2], h[3],
+                                             nloc, h[0], h[1], tr, houts[0], houts[1], tq, *g)
+
+        for o in houts:
+            o.zero_()
+        step_host()                                            # warm the staging buffers
+        barrier()
+        e_steps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            for o in houts:
+                o.zero_()
+            step_host()                                        # synchronous: returns after the D2H
+        torch.cuda.synchronize()
+        et = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(et, op=dist.ReduceOp.MAX)
+        h2d = 4 * (4 * nloc + (3 if wl["blob"] else 2) * nloc + nout * nloc) * world
+        d2h = 4 * nout * nloc * world
+        e2e = {"value": e_steps * pairs_per_step / float(et[0]), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e_steps,
+               "api": "o2d_points_on_points[_sharded](O2D_MEM_HOST) on pinned host arrays"}
+        # host path and device path must agree bit for bit
+        assert np.array_equal(houts[0][:nloc].numpy(), u), "host-memory path disagrees with device path"
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------------------
+    flops_pp = o2d.flops_per_pair(0, core, results, wl["blob"])
+    pairs_rank0 = float(nloc) * float(n)
+    kern_s = pair_ms_max * 1e-3 / args.steps          # pair-sum kernel time per step (max over ranks)
+    achieved = flops_pp * pairs_rank0 / kern_s / 1e12 if kern_s > 0 else 0.0
+    peak_nominal = info["fp32_peak_tflops"]
+    ffma = ctx.measure_fp32_peak(False)
+    ffma2 = ctx.measure_fp32_peak(True)
+    roofline = {
+        "bound": "fp32", "achieved": achieved, "peak": peak_nominal, "unit": "TFLOP/s",
+        "frac": achieved / peak_nominal if peak_nominal else None, "traffic": None,
+        "flops_per_pair": flops_pp, "kernel": f"pp_kernel<{core},res{results}>",
+        "kernel_ms_per_step": kern_s * 1e3,
+        "peak_source": f"nominal: {info['sm_count']} SMs x 128 lanes x 2 x {info['sm_clock_mhz']} MHz "
+                       "(MEASURED_PEAKS.json has no FP32 non-tensor entry; its hbm/bf16 peaks do not bound this kernel)",
+        "measured_ffma_tflops": ffma, "measured_ffma2_tflops": ffma2,
+        "frac_of_measured_ffma2": achieved / ffma2 if ffma2 else None,
+        "note": "flops are the reference's own per-pair counters (src/Kernels.h, src/CoreFunc.h), not hardware ops",
+    }
+
+    # ---- parity spot check + CPU baseline (oracle used as checker / reported baseline only) -------------------
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        kind, run, count = cpu_sample(wl, parts, args.cpu_seconds)
+        dt, sub, ref_out = run(count)
+        scale = np.sqrt(u.astype(np.float64) ** 2 + v.astype(np.float64) ** 2).max()
+        err = np.sqrt((u[sub] - ref_out[0]).astype(np.float64) ** 2 + (v[sub] - ref_out[1]).astype(np.float64) ** 2).max() / scale
+        cpu = {"value": count * n / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
+               "sample": f"{count} strided targets x all {n} sources, one call, OpenMP on all host cores, USE_VC off",
+               "seconds": dt, "max_rel_err_gpu_vs_cpu": float(err), "tolerance": 1e-5}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "f32 pair terms, f64 accumulation", "data": "synthetic",
+        "config": {"workload": wl["desc"], "particles": n, "particles_per_gpu": nblock, "core": core,
+                   "results": results, "pairs_per_step": pairs_per_step, "l2": "flushed between timed iterations (256 MB write)",
+                   "parallelism": "single GPU" if world == 1 else f"targets sharded in {world} contiguous blocks, "
+                                  "sources all-gathered (NCCL) once per step"},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": cnt["launches"],
+        "clocks": clocks, "wall_s_timed_region": wall,
+        "frac_fp32_peak_whole_step": flops_pp * value / world / 1e12 / peak_nominal,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    wl = WORKLOADS[args.workload]
+    n1 = args.n or wl["n"]
+    if args.impl == "reference":
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        n = n1 if (world == 1 or args.scaling == "strong") else sharding.weak_scaling_count(n1, world)
+        run_reference_arm(args, wl, n)
+        return
+    run_ours(args, wl, n1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,209 @@
+/*
+ * omega2d_b200.h -- C ABI of the B200-native Omega2D Biot-Savart direct-sum library.
+ *
+ * This is the drop-in boundary for ONE path of Omega2D: the O(N^2) influence sums that
+ * Convection::find_vels / find_vort and solve_bem run every Runge-Kutta substep
+ * (reference src/Convection.h:134-223, src/BEMHelper.h:96-99).  Each entry point below
+ * replaces one reference template loop nest; citations are reference file:line.
+ *
+ * Conventions shared by every call (they are the reference's, src/Influence.h:82-98 and
+ * src/Convection.h:202-216):
+ *   - float32 structure-of-arrays, counts as int, node indices as uint32 (reference
+ *     src/Omega2D.h:26 "using Int = uint32_t");
+ *   - results are ACCUMULATED into the output arrays ("tu[i] += sum") on the raw,
+ *     un-normalised sums: no 1/(2 pi), no freestream -- those are applied once per target
+ *     collection by o2d_finalize_vels, as ElementBase::finalize_vels does;
+ *   - pair terms are evaluated in float32; running sums are folded into float64 once per
+ *     source tile, then added to the float32 output ("float += double"), reproducing the
+ *     USE_VC-off STORE=float / ACCUM=double configuration (reference src/Simulation.h:44-50);
+ *   - arrays are caller-owned and only read/written during the call; the library keeps no
+ *     pointer after returning;
+ *   - `mem` says where ALL array arguments of that call live: O2D_MEM_HOST (pageable or
+ *     pinned host memory; the library stages H2D/D2H itself) or O2D_MEM_DEVICE (device
+ *     memory of the context's GPU; the call is asynchronous on the context's stream);
+ *   - every function returns O2D_OK (0) or a negative o2d_status; o2d_last_error() gives
+ *     the message.  Nothing throws across this boundary.  There is NO CPU fallback: if no
+ *     sm_100 device is usable, o2d_create fails.
+ *   - one context per (host thread, GPU); calls on one context must be sequential, which is
+ *     how the reference calls the path (src/Simulation.cpp:679-682).
+ */
+#ifndef OMEGA2D_B200_H
+#define OMEGA2D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct o2d_context o2d_context;
+
+typedef enum o2d_status {
+  O2D_OK = 0,
+  O2D_ERR_INVALID = -1,     /* bad argument (null pointer, negative count, unknown enum)   */
+  O2D_ERR_UNSUPPORTED = -2, /* results type the reference asserts against (psi)            */
+  O2D_ERR_CUDA = -3,        /* CUDA runtime error, message in o2d_last_error               */
+  O2D_ERR_NO_DEVICE = -4,   /* no sm_100 GPU: there is no CPU fallback                     */
+  O2D_ERR_COMM = -5         /* NCCL error or communicator not initialised                  */
+} o2d_status;
+
+/* core (regularisation) function: the five compile-time choices of reference
+ * src/CoreFunc.h:35-39, here a run-time argument.  O2D_CORE_V2 is the reference's default. */
+typedef enum o2d_core {
+  O2D_CORE_RM = 0,  /* Rosenhead-Moore            src/CoreFunc.h:42-82   */
+  O2D_CORE_EXP = 1, /* compact exponential        src/CoreFunc.h:85-181  */
+  O2D_CORE_WL = 2,  /* Winckelmans-Leonard        src/CoreFunc.h:184-230 */
+  O2D_CORE_V2 = 3,  /* Vatistas n=2 (default)     src/CoreFunc.h:233-275 */
+  O2D_CORE_V3 = 4   /* Vatistas n=3               src/CoreFunc.h:278-322 */
+} o2d_core;
+
+/* results type: numeric values are the reference's results_t (src/ResultsType.h:25-31) */
+typedef enum o2d_results {
+  O2D_VELONLY = 1,
+  O2D_VELANDGRAD = 2, /* kernelug_0v_0b, defined but never driven by the reference (Kernels.h:112-133) */
+  O2D_PSIONLY = 3,    /* unsupported here exactly as in the reference (Influence.h:60)     */
+  O2D_VELANDVORT = 4,
+  O2D_VELANDSHEAR = 5
+} o2d_results;
+
+typedef enum o2d_mem { O2D_MEM_HOST = 0, O2D_MEM_DEVICE = 1 } o2d_mem;
+
+/* ---- context --------------------------------------------------------------------------- */
+
+/* Create a context on CUDA device `device` (ordinal).  Fails with O2D_ERR_NO_DEVICE when
+ * the device is missing or is not compute capability 10.x. */
+int o2d_create(o2d_context** ctx, int device);
+int o2d_destroy(o2d_context* ctx);
+/* Message of the most recent failure on this thread (never NULL). */
+const char* o2d_last_error(void);
+/* Use the caller's CUDA stream (a cudaStream_t passed as void*) for all work of this
+ * context; NULL restores the context's own non-blocking stream. */
+int o2d_set_stream(o2d_context* ctx, void* cuda_stream);
+/* Block until all work queued by this context has finished. */
+int o2d_synchronize(o2d_context* ctx);
+
+/* ---- the influence sums ---------------------------------------------------------------- */
+
+/*
+ * Vortex particles on points.  Replaces points_affect_points<S,A> (reference
+ * src/Influence.h:56-416; pair kernels src/Kernels.h:81-231; cores src/CoreFunc.h).
+ *   sources: ns particles  sx,sy (position) ss (strength) sr (core radius)
+ *   targets: nt points     tx,ty and tr (core radius) or tr==NULL for inert field points
+ *            (the reference's targ.is_inert() branch, the *_0p kernels)
+ *   outputs, all accumulated into:
+ *     tu,tv             always
+ *     tq                vorticity (O2D_VELANDVORT) or shear rate (O2D_VELANDSHEAR); else NULL
+ *     tux,tvx,tuy,tvy   du/dx, dv/dx, du/dy, dv/dy (O2D_VELANDGRAD); else NULL
+ * Self pairs are included exactly like the reference: they add 0 to tu,tv and the core's
+ * d=0 value to tq.  With O2D_CORE_EXP the gradient-type results are NaN for coincident
+ * pairs, as in the reference (src/CoreFunc.h:156-166).
+ */
+int o2d_points_on_points(o2d_context* ctx, int core, int results, int mem,
+                         int ns, const float* sx, const float* sy, const float* ss, const float* sr,
+                         int nt, const float* tx, const float* ty, const float* tr,
+                         float* tu, float* tv, float* tq,
+                         float* tux, float* tvx, float* tuy, float* tvy);
+
+/*
+ * Vortex(+source) panels on points.  Replaces panels_affect_points<S,A> (reference
+ * src/Influence.h:422-614; kernelu_1vs_0p src/Kernels.h:362-405, kernelu_1v_0p :312-354).
+ *   panels: np panels over nnodes nodes nx,ny; idx[2j],idx[2j+1] are panel j's end nodes;
+ *           vs vortex-sheet strength, ss source-sheet strength or NULL (vortex only).
+ */
+int o2d_panels_on_points(o2d_context* ctx, int mem,
+                         int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                         const float* vs, const float* ss,
+                         int nt, const float* tx, const float* ty, float* tu, float* tv);
+
+/*
+ * Vortex particles on panel centres by reciprocity.  Replaces points_affect_panels<S,A>
+ * (reference src/Influence.h:633-771): pu[i] -= (1/area[i]) * sum_j kernelu_1v_0p(panel i
+ * as source with strength ss[j], particle j as target).  area = Surfaces::get_area().
+ */
+int o2d_points_on_panels(o2d_context* ctx, int mem,
+                         int ns, const float* sx, const float* sy, const float* ss,
+                         int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                         const float* area, float* pu, float* pv);
+
+/*
+ * Gaussian vorticity of particles at points.  Replaces points_affect_points_vorticity<S,A>
+ * (reference src/InfluenceVort.h:47-126): tw[i] += sum_j 2 ss_j exp(-d^2/sr_j^2)/sr_j^2.
+ */
+int o2d_points_vorticity(o2d_context* ctx, int mem,
+                         int ns, const float* sx, const float* sy, const float* ss, const float* sr,
+                         int nt, const float* tx, const float* ty, float* tw);
+
+/* ElementBase::zero_vels (reference src/ElementBase.h:200-212): u=v=0, and w,e if non-NULL. */
+int o2d_zero_vels(o2d_context* ctx, int mem, int n, float* u, float* v, float* w, float* e);
+/* ElementBase::finalize_vels (reference src/ElementBase.h:215-234): u = fs + u/(2 pi) in
+ * double, stored float; w,e (if non-NULL) scaled by 1/(2 pi). */
+int o2d_finalize_vels(o2d_context* ctx, int mem, int n, float* u, float* v, float* w, float* e,
+                      double fsx, double fsy);
+
+/* ---- the reference's existing plugin seam ---------------------------------------------- */
+
+/*
+ * Drop-in definitions of the two symbols Omega2D binds when built with
+ * -DEXTERNAL_VEL_SOLVE (reference src/Influence.h:31-35, call sites :82-88; the stock
+ * implementation is onbody's treecode, extern/onbody/src/interface2dvort.cpp:182-187 and
+ * interface2dvorttr.cpp:177-183).  Same Fortran-style signature (counts by pointer, note
+ * ss BEFORE sr), same semantics: velocities are accumulated into tu,tv, the return value is
+ * the flop count the caller turns into its GFlop/s print (negative on failure).  They use a
+ * lazily created process-wide context on device $O2D_DEVICE (default 0) and the core set by
+ * o2d_set_default_core / $O2D_CORE (rm|exp|wl|v2|v3; default v2 like the reference).
+ */
+float external_vel_solver_f_(int* ns, const float* sx, const float* sy, const float* ss, const float* sr,
+                             int* nt, const float* tx, const float* ty, float* tu, float* tv);
+float external_vel_solver_tr_f_(int* ns, const float* sx, const float* sy, const float* ss, const float* sr,
+                                int* nt, const float* tx, const float* ty, const float* tr,
+                                float* tu, float* tv);
+int o2d_set_default_core(int core);
+int o2d_get_default_core(void);
+
+/* ---- multi-GPU: targets sharded in contiguous blocks, sources all-gathered -------------- */
+
+/* 128-byte NCCL unique id; rank 0 creates it, the host program distributes it. */
+#define O2D_UNIQUE_ID_BYTES 128
+int o2d_comm_unique_id(void* id128);
+/* Join communicator of `nranks` ranks as `rank` (one context / process / GPU per rank). */
+int o2d_comm_init(o2d_context* ctx, int nranks, int rank, const void* id128);
+int o2d_comm_destroy(o2d_context* ctx);
+/*
+ * Sharded points-on-points: this rank owns ns_local source particles (its block of the
+ * global set) and nt target points.  Each rank's packed source block is replicated to every
+ * rank with ONE ncclAllGather over NVLink (16 B per particle), overlapped with the sum over
+ * the rank's own block; outputs stay on the owning rank.  ns_block is the per-rank block
+ * capacity agreed by all ranks (>= every rank's ns_local, e.g. ceil(N/nranks)).
+ * Same argument meaning as o2d_points_on_points otherwise.
+ */
+int o2d_points_on_points_sharded(o2d_context* ctx, int core, int results, int mem,
+                                 int ns_local, int ns_block,
+                                 const float* sx, const float* sy, const float* ss, const float* sr,
+                                 int nt, const float* tx, const float* ty, const float* tr,
+                                 float* tu, float* tv, float* tq,
+                                 float* tux, float* tvx, float* tuy, float* tvy);
+
+/* ---- measurement hooks (used by bench.py; no effect on results) ------------------------- */
+
+/* Reference ("algorithmic") flops per pair, from the reference's own counters
+ * (src/Kernels.h flops*_*(), src/CoreFunc.h flops_t{p,v}_{no,}grads()).
+ * kind: 0 points-on-points (uses core, results, blob_targets), 1 panels vortex-only,
+ * 2 panels vortex+source, 3 Gaussian vorticity. */
+int o2d_flops_per_pair(int kind, int core, int results, int blob_targets);
+/* Kernel launch counter and CUDA-event timing of the dominant (pair-sum) kernels, measured
+ * on the stream they are launched on.  Timing is off by default. */
+int o2d_enable_timing(o2d_context* ctx, int on);
+int o2d_reset_counters(o2d_context* ctx);
+int o2d_get_counters(o2d_context* ctx, long long* kernel_launches, long long* pair_kernel_launches,
+                     double* pair_kernel_ms);
+/* Device facts: SM count, max SM clock (MHz), nominal FP32 peak = SMs*128*2*clock (TFLOP/s). */
+int o2d_device_info(o2d_context* ctx, int* sm_count, int* sm_clock_mhz, double* fp32_peak_tflops);
+/* Sustained FP32 throughput of a dependent-chain-free FFMA (packed=0) or FFMA2 (packed=1)
+ * micro-kernel on this device, in TFLOP/s (2 flops per lane-FMA). */
+int o2d_measure_fp32_peak(o2d_context* ctx, int packed, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OMEGA2D_B200_H */

@@ -1,0 +1,288 @@
+"""omega2d_b200 -- B200-native direct-sum Biot-Savart evaluation for Omega2D.
+
+The product is the C-ABI shared library ``libomega2d_b200.so`` (sources in
+``omega2d_b200/csrc``, ABI in ``include/omega2d_b200.h``) plus the C++ header mirror of the
+reference's influence interface in ``omega2d_b200/host``.  This Python package is harness
+glue only: a ctypes binding used by ``tests/``, ``bench.py`` and ``__graft_entry__.py``.
+
+There is no CPU fallback anywhere in this package: if the library is missing, or no sm_100
+GPU is present, creating a :class:`Context` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB_PATH = os.path.join(HERE, "libomega2d_b200.so")
+HEADER_PATH = os.path.join(ROOT, "include", "omega2d_b200.h")
+
+CORES = ("rm", "exp", "wl", "v2", "v3")
+CORE_ID = {n: i for i, n in enumerate(CORES)}
+# reference results_t (reference src/ResultsType.h:25-31)
+VELONLY, VELANDGRAD, PSIONLY, VELANDVORT, VELANDSHEAR = 1, 2, 3, 4, 5
+MEM_HOST, MEM_DEVICE = 0, 1
+OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE, ERR_COMM = 0, -1, -2, -3, -4, -5
+
+_fp = C.POINTER(C.c_float)
+_up = C.POINTER(C.c_uint32)
+
+
+class O2DError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"omega2d_b200 error {code}: {msg}")
+        self.code = code
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libomega2d_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(HERE, "csrc"), "-j", str(max(2, os.cpu_count() or 2))]
+    res = subprocess.run(cmd, capture_output=not verbose, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("building libomega2d_b200.so failed:\n" + (res.stdout or "") + (res.stderr or ""))
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen the product library.  Raises if it has not been built -- never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(omega2d_b200 has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i, d = C.c_void_p, C.c_int, C.c_double
+    lib.o2d_last_error.restype = C.c_char_p
+    lib.o2d_create.argtypes = [C.POINTER(vp), i]
+    lib.o2d_destroy.argtypes = [vp]
+    lib.o2d_set_stream.argtypes = [vp, vp]
+    lib.o2d_synchronize.argtypes = [vp]
+    pp = [vp, i, i, i, i, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.o2d_points_on_points.argtypes = pp
+    lib.o2d_points_on_points_sharded.argtypes = [vp, i, i, i, i, i, vp, vp, vp, vp, i, vp, vp, vp,
+                                                 vp, vp, vp, vp, vp, vp, vp]
+    lib.o2d_panels_on_points.argtypes = [vp, i, i, i, vp, vp, vp, vp, vp, i, vp, vp, vp, vp]
+    lib.o2d_points_on_panels.argtypes = [vp, i, i, vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp]
+    lib.o2d_points_vorticity.argtypes = [vp, i, i, vp, vp, vp, vp, i, vp, vp, vp]
+    lib.o2d_zero_vels.argtypes = [vp, i, i, vp, vp, vp, vp]
+    lib.o2d_finalize_vels.argtypes = [vp, i, i, vp, vp, vp, vp, d, d]
+    lib.external_vel_solver_f_.restype = C.c_float
+    lib.external_vel_solver_f_.argtypes = [C.POINTER(i), vp, vp, vp, vp, C.POINTER(i), vp, vp, vp, vp]
+    lib.external_vel_solver_tr_f_.restype = C.c_float
+    lib.external_vel_solver_tr_f_.argtypes = [C.POINTER(i), vp, vp, vp, vp, C.POINTER(i), vp, vp, vp, vp, vp]
+    lib.o2d_set_default_core.argtypes = [i]
+    lib.o2d_comm_unique_id.argtypes = [vp]
+    lib.o2d_comm_init.argtypes = [vp, i, i, vp]
+    lib.o2d_comm_destroy.argtypes = [vp]
+    lib.o2d_flops_per_pair.argtypes = [i, i, i, i]
+    lib.o2d_enable_timing.argtypes = [vp, i]
+    lib.o2d_reset_counters.argtypes = [vp]
+    lib.o2d_get_counters.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(d)]
+    lib.o2d_device_info.argtypes = [vp, C.POINTER(i), C.POINTER(i), C.POINTER(d)]
+    lib.o2d_measure_fp32_peak.argtypes = [vp, i, C.POINTER(d)]
+    _lib = lib
+    return lib
+
+
+def flops_per_pair(kind: int, core: str = "rm", results: int = VELONLY, blob_targets: bool = True) -> int:
+    return int(load_library().o2d_flops_per_pair(kind, CORE_ID[core], results, int(blob_targets)))
+
+
+def _ptr(a):
+    """numpy array / torch tensor / int address / None -> integer address (or None)."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        assert a.flags.c_contiguous, "arrays must be contiguous"
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):   # torch tensor (host or device)
+        assert a.is_contiguous(), "tensors must be contiguous"
+        return a.data_ptr()
+    raise TypeError(f"cannot take the address of {type(a)}")
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Context:
+    """One library context = one GPU.  Methods mirror the C ABI one to one; the ``*_np``
+    helpers take/return numpy arrays through the O2D_MEM_HOST path (what an unmodified
+    Omega2D would use: caller-owned host std::vector storage)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self._h = C.c_void_p()
+        rc = self.lib.o2d_create(C.byref(self._h), int(device))
+        if rc != OK:
+            raise O2DError(rc, self.lib.o2d_last_error().decode())
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.o2d_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != OK:
+            raise O2DError(rc, self.lib.o2d_last_error().decode())
+
+    # -- plumbing
+    def set_stream(self, stream_handle):
+        self._check(self.lib.o2d_set_stream(self._h, stream_handle))
+
+    def synchronize(self):
+        self._check(self.lib.o2d_synchronize(self._h))
+
+    def enable_timing(self, on=True):
+        self._check(self.lib.o2d_enable_timing(self._h, int(on)))
+
+    def reset_counters(self):
+        self._check(self.lib.o2d_reset_counters(self._h))
+
+    def counters(self):
+        a, b, ms = C.c_longlong(), C.c_longlong(), C.c_double()
+        self._check(self.lib.o2d_get_counters(self._h, C.byref(a), C.byref(b), C.byref(ms)))
+        return {"launches": a.value, "pair_launches": b.value, "pair_ms": ms.value}
+
+    def device_info(self):
+        sm, mhz, pk = C.c_int(), C.c_int(), C.c_double()
+        self._check(self.lib.o2d_device_info(self._h, C.byref(sm), C.byref(mhz), C.byref(pk)))
+        return {"sm_count": sm.value, "sm_clock_mhz": mhz.value, "fp32_peak_tflops": pk.value}
+
+    def measure_fp32_peak(self, packed: bool) -> float:
+        t = C.c_double()
+        self._check(self.lib.o2d_measure_fp32_peak(self._h, int(packed), C.byref(t)))
+        return t.value
+
+    # -- raw C-ABI calls (pointers may be numpy arrays, torch tensors or integer addresses)
+    def points_on_points(self, core, results, mem, ns, sx, sy, ss, sr, nt, tx, ty, tr, tu, tv,
+                         tq=None, tux=None, tvx=None, tuy=None, tvy=None):
+        core = CORE_ID[core] if isinstance(core, str) else int(core)
+        self._check(self.lib.o2d_points_on_points(
+            self._h, core, int(results), int(mem), int(ns), _ptr(sx), _ptr(sy), _ptr(ss), _ptr(sr),
+            int(nt), _ptr(tx), _ptr(ty), _ptr(tr), _ptr(tu), _ptr(tv), _ptr(tq),
+            _ptr(tux), _ptr(tvx), _ptr(tuy), _ptr(tvy)))
+
+    def points_on_points_sharded(self, core, results, mem, ns_local, ns_block, sx, sy, ss, sr, nt,
+                                 tx, ty, tr, tu, tv, tq=None, tux=None, tvx=None, tuy=None, tvy=None):
+        core = CORE_ID[core] if isinstance(core, str) else int(core)
+        self._check(self.lib.o2d_points_on_points_sharded(
+            self._h, core, int(results), int(mem), int(ns_local), int(ns_block),
+            _ptr(sx), _ptr(sy), _ptr(ss), _ptr(sr), int(nt), _ptr(tx), _ptr(ty), _ptr(tr),
+            _ptr(tu), _ptr(tv), _ptr(tq), _ptr(tux), _ptr(tvx), _ptr(tuy), _ptr(tvy)))
+
+    def panels_on_points(self, mem, np_, nnodes, nx, ny, idx, vs, ss, nt, tx, ty, tu, tv):
+        self._check(self.lib.o2d_panels_on_points(
+            self._h, int(mem), int(np_), int(nnodes), _ptr(nx), _ptr(ny), _ptr(idx), _ptr(vs), _ptr(ss),
+            int(nt), _ptr(tx), _ptr(ty), _ptr(tu), _ptr(tv)))
+
+    def points_on_panels(self, mem, ns, sx, sy, ss, np_, nnodes, nx, ny, idx, area, pu, pv):
+        self._check(self.lib.o2d_points_on_panels(
+            self._h, int(mem), int(ns), _ptr(sx), _ptr(sy), _ptr(ss), int(np_), int(nnodes),
+            _ptr(nx), _ptr(ny), _ptr(idx), _ptr(area), _ptr(pu), _ptr(pv)))
+
+    def points_vorticity(self, mem, ns, sx, sy, ss, sr, nt, tx, ty, tw):
+        self._check(self.lib.o2d_points_vorticity(
+            self._h, int(mem), int(ns), _ptr(sx), _ptr(sy), _ptr(ss), _ptr(sr), int(nt),
+            _ptr(tx), _ptr(ty), _ptr(tw)))
+
+    def zero_vels(self, mem, n, u, v, w=None, e=None):
+        self._check(self.lib.o2d_zero_vels(self._h, int(mem), int(n), _ptr(u), _ptr(v), _ptr(w), _ptr(e)))
+
+    def finalize_vels(self, mem, n, u, v, w=None, e=None, fs=(0.0, 0.0)):
+        self._check(self.lib.o2d_finalize_vels(self._h, int(mem), int(n), _ptr(u), _ptr(v), _ptr(w), _ptr(e),
+                                               float(fs[0]), float(fs[1])))
+
+    # -- comm
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        lib = load_library()
+        buf = C.create_string_buffer(128)
+        rc = lib.o2d_comm_unique_id(buf)
+        if rc != OK:
+            raise O2DError(rc, lib.o2d_last_error().decode())
+        return buf.raw
+
+    def comm_init(self, nranks: int, rank: int, uid: bytes):
+        assert len(uid) == 128
+        buf = C.create_string_buffer(uid, 128)
+        self._check(self.lib.o2d_comm_init(self._h, int(nranks), int(rank), buf))
+
+    # -- numpy conveniences over the host-memory path (same argument order as the oracle wrappers)
+    def points_on_points_np(self, core, results, sx, sy, ss, sr, tx, ty, tr=None, init=None):
+        sx, sy, ss, sr, tx, ty, tr = map(_f32, (sx, sy, ss, sr, tx, ty, tr))
+        nt = tx.size
+        nout = {VELONLY: 2, VELANDVORT: 3, VELANDSHEAR: 3, VELANDGRAD: 6}.get(results, 2)
+        outs = [np.zeros(nt, np.float32) for _ in range(nout)]
+        if init is not None:
+            for o, i0 in zip(outs, init):
+                o[:] = i0
+        tq = outs[2] if nout == 3 else None
+        g = outs[2:6] if nout == 6 else [None] * 4
+        self.points_on_points(core, results, MEM_HOST, sx.size, sx, sy, ss, sr, nt, tx, ty, tr,
+                              outs[0], outs[1], tq, *g)
+        return tuple(outs)
+
+    def panels_on_points_np(self, nx, ny, idx, vs, ss, tx, ty, init=None):
+        nx, ny, vs, ss, tx, ty = map(_f32, (nx, ny, vs, ss, tx, ty))
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        nt = tx.size
+        tu, tv = np.zeros(nt, np.float32), np.zeros(nt, np.float32)
+        if init is not None:
+            tu[:], tv[:] = init
+        self.panels_on_points(MEM_HOST, vs.size, nx.size, nx, ny, idx, vs, ss, nt, tx, ty, tu, tv)
+        return tu, tv
+
+    def points_on_panels_np(self, sx, sy, ss, nx, ny, idx, area, init=None):
+        sx, sy, ss, nx, ny, area = map(_f32, (sx, sy, ss, nx, ny, area))
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        npan = idx.size // 2
+        pu, pv = np.zeros(npan, np.float32), np.zeros(npan, np.float32)
+        if init is not None:
+            pu[:], pv[:] = init
+        self.points_on_panels(MEM_HOST, sx.size, sx, sy, ss, npan, nx.size, nx, ny, idx, area, pu, pv)
+        return pu, pv
+
+    def points_vorticity_np(self, sx, sy, ss, sr, tx, ty, init=None):
+        sx, sy, ss, sr, tx, ty = map(_f32, (sx, sy, ss, sr, tx, ty))
+        tw = np.zeros(tx.size, np.float32)
+        if init is not None:
+            tw[:] = init
+        self.points_vorticity(MEM_HOST, sx.size, sx, sy, ss, sr, tx.size, tx, ty, tw)
+        return tw
+
+
+def external_vel_solver(sx, sy, ss, sr, tx, ty, tr=None, tu=None, tv=None):
+    """Call the legacy plugin symbols exactly as Omega2D does (reference src/Influence.h:82-88)."""
+    lib = load_library()
+    sx, sy, ss, sr, tx, ty, tr = map(_f32, (sx, sy, ss, sr, tx, ty, tr))
+    ns, nt = C.c_int(sx.size), C.c_int(tx.size)
+    tu = np.zeros(tx.size, np.float32) if tu is None else np.array(tu, np.float32)
+    tv = np.zeros(tx.size, np.float32) if tv is None else np.array(tv, np.float32)
+    if tr is None:
+        flops = lib.external_vel_solver_f_(C.byref(ns), _ptr(sx), _ptr(sy), _ptr(ss), _ptr(sr),
+                                           C.byref(nt), _ptr(tx), _ptr(ty), _ptr(tu), _ptr(tv))
+    else:
+        flops = lib.external_vel_solver_tr_f_(C.byref(ns), _ptr(sx), _ptr(sy), _ptr(ss), _ptr(sr),
+                                              C.byref(nt), _ptr(tx), _ptr(ty), _ptr(tr), _ptr(tu), _ptr(tv))
+    if flops < 0:
+        raise O2DError(int(flops), lib.o2d_last_error().decode())
+    return tu, tv, float(flops)

@@ -1,0 +1,884 @@
+// o2d_api.cu -- the C ABI declared in include/omega2d_b200.h: context, device mirrors of
+// host arrays, launch planning, NCCL source all-gather, measurement hooks.
+#include "../../include/omega2d_b200.h"
+#include "o2d_internal.h"
+
+#include <dlfcn.h>
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace o2d;
+
+// ---- errors --------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(O2D_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// ---- grow-only device buffer -----------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaError_t e = cudaFree(p); if (e != cudaSuccess) return e; p = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) return e;
+    cap = want;
+    return cudaSuccess;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+// ---- NCCL through dlopen (no link-time dependency; single-GPU users never load it) -------------
+typedef struct ncclComm* ncclComm_t;
+struct NcclUid { char internal[128]; };
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(NcclUid*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, NcclUid, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool load() {
+    if (handle) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (handle) break; }
+    if (!handle) return false;
+    GetUniqueId = (decltype(GetUniqueId))dlsym(handle, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(handle, "ncclCommInitRank");
+    CommDestroy = (decltype(CommDestroy))dlsym(handle, "ncclCommDestroy");
+    AllGather = (decltype(AllGather))dlsym(handle, "ncclAllGather");
+    GetErrorString = (decltype(GetErrorString))dlsym(handle, "ncclGetErrorString");
+    return GetUniqueId && CommInitRank && CommDestroy && AllGather && GetErrorString;
+  }
+};
+static NcclApi g_nccl;
+static std::mutex g_nccl_mu;
+constexpr int kNcclChar = 0;  // ncclInt8 / ncclChar
+
+// ---- context -----------------------------------------------------------------------------------------
+struct o2d_context {
+  int device = 0;
+  int sm_count = 0;
+  int sm_clock_khz = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t comm_stream = nullptr;
+  cudaStream_t stream = nullptr;   // stream in use (own or caller's)
+  cudaEvent_t ev_gather = nullptr, ev_pack = nullptr;
+  // scratch
+  DevBuf packed, packed_all, partial, panel_packed;
+  DevBuf hsrc, htgt, hout, hidx;   // device mirrors for O2D_MEM_HOST calls
+  // comm
+  ncclComm_t comm = nullptr;
+  int nranks = 1, rank = 0;
+  // counters
+  long long launches = 0, pair_launches = 0;
+  double pair_ms = 0.0;
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool, ev_pending;
+};
+
+static int bind_device(o2d_context* c) {
+  CU(cudaSetDevice(c->device));
+  return O2D_OK;
+}
+
+static int drain_timing(o2d_context* c) {
+  for (auto& pr : c->ev_pending) {
+    CU(cudaEventSynchronize(pr.second));
+    float ms = 0.0f;
+    CU(cudaEventElapsedTime(&ms, pr.first, pr.second));
+    c->pair_ms += ms;
+    c->ev_pool.push_back(pr);
+  }
+  c->ev_pending.clear();
+  return O2D_OK;
+}
+
+struct PairTimer {   // brackets the dominant kernel launches with events on the launching stream
+  o2d_context* c;
+  std::pair<cudaEvent_t, cudaEvent_t> pr{nullptr, nullptr};
+  explicit PairTimer(o2d_context* ctx) : c(ctx) {
+    if (!c->timing) return;
+    if (c->ev_pending.size() >= 512) drain_timing(c);
+    if (c->ev_pool.empty()) {
+      cudaEventCreate(&pr.first);
+      cudaEventCreate(&pr.second);
+    } else {
+      pr = c->ev_pool.back();
+      c->ev_pool.pop_back();
+    }
+    cudaEventRecord(pr.first, c->stream);
+  }
+  ~PairTimer() {
+    if (!c->timing || !pr.first) return;
+    cudaEventRecord(pr.second, c->stream);
+    c->ev_pending.push_back(pr);
+  }
+};
+
+extern "C" const char* o2d_last_error(void) { return g_err; }
+
+extern "C" int o2d_create(o2d_context** out, int device) {
+  if (!out) return fail(O2D_ERR_INVALID, "o2d_create: ctx is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0)
+    return fail(O2D_ERR_NO_DEVICE, "no CUDA device (%s); omega2d_b200 has no CPU fallback",
+                e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(O2D_ERR_NO_DEVICE, "device %d out of range (have %d)", device, ndev);
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(O2D_ERR_NO_DEVICE, "device %d is sm_%d%d; this library only carries sm_100a code", device,
+                prop.major, prop.minor);
+  o2d_context* c = new o2d_context();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  cudaDeviceGetAttribute(&c->sm_clock_khz, cudaDevAttrClockRate, device);
+  CU(cudaSetDevice(device));
+  CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&c->ev_gather, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming));
+  c->stream = c->own_stream;
+  *out = c;
+  return O2D_OK;
+}
+
+extern "C" int o2d_comm_destroy(o2d_context* c);
+
+extern "C" int o2d_destroy(o2d_context* c) {
+  if (!c) return O2D_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  o2d_comm_destroy(c);
+  for (DevBuf* b : {&c->packed, &c->packed_all, &c->partial, &c->panel_packed, &c->hsrc, &c->htgt, &c->hout, &c->hidx})
+    b->release();
+  for (auto& pr : c->ev_pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  for (auto& pr : c->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  cudaEventDestroy(c->ev_gather);
+  cudaEventDestroy(c->ev_pack);
+  cudaStreamDestroy(c->own_stream);
+  cudaStreamDestroy(c->comm_stream);
+  delete c;
+  return O2D_OK;
+}
+
+extern "C" int o2d_set_stream(o2d_context* c, void* s) {
+  if (!c) return fail(O2D_ERR_INVALID, "ctx is NULL");
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return O2D_OK;
+}
+
+extern "C" int o2d_synchronize(o2d_context* c) {
+  if (!c) return fail(O2D_ERR_INVALID, "ctx is NULL");
+  if (int rc = bind_device(c)) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  return O2D_OK;
+}
+
+// ---- launch planning -----------------------------------------------------------------------------------
+// Pick the number of source chunks (grid.y) so that the last wave of CTAs is nearly full.
+// nb target blocks x nchunks chunks run on `slots` = SMs x resident CTAs; a chunk costs
+// ceil(ntiles/nchunks) tiles.  Efficiency = useful tile-slots / scheduled tile-slots.
+static int choose_chunks(int nb, int ntiles, int slots, int max_chunks) {
+  if (ntiles <= 1 || nb <= 0) return 1;
+  int best = 1;
+  double best_eff = 0.0;
+  const int limit = std::min(ntiles, max_chunks);
+  for (int nc = 1; nc <= limit; ++nc) {
+    const int tpc = (ntiles + nc - 1) / nc;
+    const int real_nc = (ntiles + tpc - 1) / tpc;
+    if (real_nc != nc) continue;
+    const long long items = (long long)nb * nc;
+    const long long waves = (items + slots - 1) / slots;
+    double eff = ((double)nb * ntiles) / ((double)waves * tpc * slots);
+    // prefer fewer chunks at equal efficiency (each chunk re-reads targets and writes partials)
+    eff -= 0.0005 * nc;
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = nc; }
+    if (best_eff > 0.985) break;
+  }
+  return best;
+}
+
+static int res_from_results(int results) {
+  switch (results) {
+    case O2D_VELONLY: return RES_U;
+    case O2D_VELANDVORT: return RES_UW;
+    case O2D_VELANDSHEAR: return RES_UE;
+    case O2D_VELANDGRAD: return RES_UG;
+  }
+  return -1;
+}
+
+// one pair-sum launch over logical tiles [tile_begin, tile_end) of an already packed source array,
+// split into `nchunks` chunks (nchunks > 1 requires a partials buffer)
+static int pp_run_packed(o2d_context* c, int core, int res, const float4* packed,
+                         int tile_begin, int tile_end, int skip_begin, int skip_len,
+                         const float* tx, const float* ty, const float* tr, int nt, const OutPtrs& out,
+                         int* chunk_cursor, int nchunks, double* partial_base) {
+  const int ntiles = tile_end - tile_begin;
+  if (ntiles <= 0 || nt <= 0 || nchunks <= 0) return O2D_OK;
+  if (nchunks > 1 && partial_base == nullptr) return fail(O2D_ERR_INVALID, "internal: chunked launch without partials");
+  PPArgs a;
+  a.packed = packed;
+  a.tile_begin = tile_begin;
+  a.tile_end = tile_end;
+  a.skip_begin = skip_begin;
+  a.skip_len = skip_len;
+  a.tx = tx; a.ty = ty; a.tr = tr; a.nt = nt;
+  a.out = out;
+  a.partial = partial_base;
+  a.chunk_offset = chunk_cursor ? *chunk_cursor : 0;
+  a.tiles_per_chunk = (ntiles + nchunks - 1) / nchunks;
+  CU(launch_pp(core, res, a, nchunks, c->stream));
+  c->launches++;
+  c->pair_launches++;
+  if (chunk_cursor) *chunk_cursor += nchunks;
+  return O2D_OK;
+}
+
+static int pp_device(o2d_context* c, int core, int res,
+                     int ns, const float* sx, const float* sy, const float* ss, const float* sr,
+                     int nt, const float* tx, const float* ty, const float* tr, const OutPtrs& out) {
+  if (ns <= 0 || nt <= 0) return O2D_OK;
+  const int ntiles = (ns + kTile - 1) / kTile;
+  const int ns_padded = ntiles * kTile;
+  CU(c->packed.reserve((size_t)ns_padded * 16));
+  CU(launch_pack_sources(res == RES_VORT ? 100 : core, ns, sx, sy, ss, sr, c->packed.as<float4>(), ns_padded, c->stream));
+  c->launches++;
+  const int R = res_targets_per_thread(res);
+  const int nb = (nt + kThreads * R - 1) / (kThreads * R);
+  const int slots = c->sm_count * pp_occupancy(core, res);
+  const int nchunks = choose_chunks(nb, ntiles, slots, 256);
+  double* partial = nullptr;
+  if (nchunks > 1) {
+    CU(c->partial.reserve((size_t)nchunks * res_ncomp(res) * (size_t)nt * sizeof(double)));
+    partial = c->partial.as<double>();
+  }
+  {
+    PairTimer timer(c);
+    int rc = pp_run_packed(c, core, res, c->packed.as<float4>(), 0, ntiles, INT_MAX, 0, tx, ty, tr, nt, out,
+                           nullptr, nchunks, partial);
+    if (rc) return rc;
+  }
+  if (nchunks > 1) {
+    CU(launch_pp_combine(res, partial, nchunks, nt, out, c->stream));
+    c->launches++;
+  }
+  return O2D_OK;
+}
+
+// ---- host staging helpers ----------------------------------------------------------------------------------
+struct Stager {   // carve float arrays out of one device buffer
+  o2d_context* c;
+  DevBuf* buf;
+  size_t off = 0;
+  Stager(o2d_context* ctx, DevBuf* b) : c(ctx), buf(b) {}
+  float* take(size_t n) {
+    float* p = reinterpret_cast<float*>(reinterpret_cast<char*>(buf->p) + off);
+    off += ((n * sizeof(float) + 255) / 256) * 256;
+    return p;
+  }
+};
+static size_t padded_floats(size_t n) { return ((n * sizeof(float) + 255) / 256) * 256; }
+
+static int h2d(o2d_context* c, float* dst, const float* src, size_t n) {
+  if (n == 0) return O2D_OK;
+  CU(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  return O2D_OK;
+}
+static int d2h(o2d_context* c, float* dst, const float* src, size_t n) {
+  if (n == 0) return O2D_OK;
+  CU(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  return O2D_OK;
+}
+
+static int check_common(o2d_context* c, int mem) {
+  if (!c) return fail(O2D_ERR_INVALID, "ctx is NULL");
+  if (mem != O2D_MEM_HOST && mem != O2D_MEM_DEVICE) return fail(O2D_ERR_INVALID, "unknown mem space %d", mem);
+  return bind_device(c);
+}
+
+// gathers the output pointer list for a results type; returns number of outputs or <0
+static int collect_outputs(int res, float* tu, float* tv, float* tq, float* tux, float* tvx, float* tuy,
+                           float* tvy, float** outs) {
+  if (!tu || !tv) return fail(O2D_ERR_INVALID, "tu/tv must not be NULL");
+  outs[0] = tu; outs[1] = tv;
+  if (res == RES_U) return 2;
+  if (res == RES_UW || res == RES_UE) {
+    if (!tq) return fail(O2D_ERR_INVALID, "tq must not be NULL for vorticity/shear results");
+    outs[2] = tq;
+    return 3;
+  }
+  if (!tux || !tvx || !tuy || !tvy) return fail(O2D_ERR_INVALID, "gradient outputs must not be NULL for velandgrad");
+  outs[2] = tux; outs[3] = tvx; outs[4] = tuy; outs[5] = tvy;
+  return 6;
+}
+
+extern "C" int o2d_points_on_points(o2d_context* c, int core, int results, int mem,
+                                    int ns, const float* sx, const float* sy, const float* ss, const float* sr,
+                                    int nt, const float* tx, const float* ty, const float* tr,
+                                    float* tu, float* tv, float* tq,
+                                    float* tux, float* tvx, float* tuy, float* tvy) {
+  if (int rc = check_common(c, mem)) return rc;
+  if (core < 0 || core > 4) return fail(O2D_ERR_INVALID, "unknown core %d", core);
+  if (results == O2D_PSIONLY)
+    return fail(O2D_ERR_UNSUPPORTED, "Point elements cannot compute streamfunction yet (reference src/Influence.h:60)");
+  const int res = res_from_results(results);
+  if (res < 0) return fail(O2D_ERR_INVALID, "unknown results type %d", results);
+  if (ns < 0 || nt < 0) return fail(O2D_ERR_INVALID, "negative count");
+  if (ns == 0 || nt == 0) return O2D_OK;
+  if (!sx || !sy || !ss || !sr || !tx || !ty) return fail(O2D_ERR_INVALID, "NULL source/target array");
+  float* outs[kMaxOut] = {nullptr};
+  const int nout = collect_outputs(res, tu, tv, tq, tux, tvx, tuy, tvy, outs);
+  if (nout < 0) return nout;
+  OutPtrs o{};
+  if (mem == O2D_MEM_DEVICE) {
+    for (int k = 0; k < nout; ++k) o.p[k] = outs[k];
+    return pp_device(c, core, res, ns, sx, sy, ss, sr, nt, tx, ty, tr, o);
+  }
+  // host arrays: mirror on the device, run, copy the accumulated outputs back
+  CU(c->hsrc.reserve(4 * padded_floats(ns)));
+  CU(c->htgt.reserve(3 * padded_floats(nt)));
+  CU(c->hout.reserve(kMaxOut * padded_floats(nt)));
+  Stager S(c, &c->hsrc), T(c, &c->htgt), O(c, &c->hout);
+  float *dsx = S.take(ns), *dsy = S.take(ns), *dss = S.take(ns), *dsr = S.take(ns);
+  float *dtx = T.take(nt), *dty = T.take(nt), *dtr = tr ? T.take(nt) : nullptr;
+  int rc;
+  if ((rc = h2d(c, dsx, sx, ns)) || (rc = h2d(c, dsy, sy, ns)) || (rc = h2d(c, dss, ss, ns)) ||
+      (rc = h2d(c, dsr, sr, ns)) || (rc = h2d(c, dtx, tx, nt)) || (rc = h2d(c, dty, ty, nt)))
+    return rc;
+  if (tr && (rc = h2d(c, dtr, tr, nt))) return rc;
+  for (int k = 0; k < nout; ++k) {
+    o.p[k] = O.take(nt);
+    if ((rc = h2d(c, o.p[k], outs[k], nt))) return rc;
+  }
+  if ((rc = pp_device(c, core, res, ns, dsx, dsy, dss, dsr, nt, dtx, dty, dtr, o))) return rc;
+  for (int k = 0; k < nout; ++k)
+    if ((rc = d2h(c, outs[k], o.p[k], nt))) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  return O2D_OK;
+}
+
+extern "C" int o2d_points_vorticity(o2d_context* c, int mem,
+                                    int ns, const float* sx, const float* sy, const float* ss, const float* sr,
+                                    int nt, const float* tx, const float* ty, float* tw) {
+  if (int rc = check_common(c, mem)) return rc;
+  if (ns < 0 || nt < 0) return fail(O2D_ERR_INVALID, "negative count");
+  if (ns == 0 || nt == 0) return O2D_OK;
+  if (!sx || !sy || !ss || !sr || !tx || !ty || !tw) return fail(O2D_ERR_INVALID, "NULL array");
+  OutPtrs o{};
+  if (mem == O2D_MEM_DEVICE) {
+    o.p[0] = tw;
+    return pp_device(c, CORE_RM, RES_VORT, ns, sx, sy, ss, sr, nt, tx, ty, nullptr, o);
+  }
+  CU(c->hsrc.reserve(4 * padded_floats(ns)));
+  CU(c->htgt.reserve(3 * padded_floats(nt)));
+  CU(c->hout.reserve(kMaxOut * padded_floats(nt)));
+  Stager S(c, &c->hsrc), T(c, &c->htgt), O(c, &c->hout);
+  float *dsx = S.take(ns), *dsy = S.take(ns), *dss = S.take(ns), *dsr = S.take(ns);
+  float *dtx = T.take(nt), *dty = T.take(nt);
+  o.p[0] = O.take(nt);
+  int rc;
+  if ((rc = h2d(c, dsx, sx, ns)) || (rc = h2d(c, dsy, sy, ns)) || (rc = h2d(c, dss, ss, ns)) ||
+      (rc = h2d(c, dsr, sr, ns)) || (rc = h2d(c, dtx, tx, nt)) || (rc = h2d(c, dty, ty, nt)) ||
+      (rc = h2d(c, o.p[0], tw, nt)))
+    return rc;
+  if ((rc = pp_device(c, CORE_RM, RES_VORT, ns, dsx, dsy, dss, dsr, nt, dtx, dty, nullptr, o))) return rc;
+  if ((rc = d2h(c, tw, o.p[0], nt))) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  return O2D_OK;
+}
+
+// ---- panels ------------------------------------------------------------------------------------------------
+static int panels_on_points_device(o2d_context* c, int np, const float* nx, const float* ny, const uint32_t* idx,
+                                   const float* vs, const float* ss, int nt, const float* tx, const float* ty,
+                                   float* tu, float* tv) {
+  if (np <= 0 || nt <= 0) return O2D_OK;
+  const int ntiles = (np + kPanelTile - 1) / kPanelTile;
+  const int np_padded = ntiles * kPanelTile;
+  CU(c->panel_packed.reserve((size_t)np_padded * 32));
+  CU(launch_pack_panels(np, nx, ny, idx, vs, ss, c->panel_packed.as<float4>(), np_padded, c->stream));
+  c->launches++;
+  const int nb = (nt + 127) / 128;
+  const int slots = c->sm_count * panels_occupancy();
+  const int nchunks = choose_chunks(nb, ntiles, slots, 256);
+  PanelArgs a;
+  a.packed = c->panel_packed.as<float4>();
+  a.npanels_padded = np_padded;
+  a.tiles_per_chunk = (ntiles + nchunks - 1) / nchunks;
+  a.tx = tx; a.ty = ty; a.nt = nt;
+  a.out = OutPtrs{};
+  a.out.p[0] = tu; a.out.p[1] = tv;
+  a.partial = nullptr;
+  if (nchunks > 1) {
+    CU(c->partial.reserve((size_t)nchunks * 2 * (size_t)nt * sizeof(double)));
+    a.partial = c->partial.as<double>();
+  }
+  {
+    PairTimer timer(c);
+    CU(launch_panels_on_points(a, nchunks, c->stream));
+    c->launches++;
+    c->pair_launches++;
+  }
+  if (nchunks > 1) {
+    CU(launch_panels_combine(a.partial, nchunks, nt, a.out, c->stream));
+    c->launches++;
+  }
+  return O2D_OK;
+}
+
+extern "C" int o2d_panels_on_points(o2d_context* c, int mem,
+                                    int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                                    const float* vs, const float* ss,
+                                    int nt, const float* tx, const float* ty, float* tu, float* tv) {
+  if (int rc = check_common(c, mem)) return rc;
+  if (np < 0 || nt < 0 || nnodes < 0) return fail(O2D_ERR_INVALID, "negative count");
+  if (np == 0 || nt == 0) return O2D_OK;
+  if (!nx || !ny || !idx || !vs || !tx || !ty || !tu || !tv) return fail(O2D_ERR_INVALID, "NULL array");
+  if (mem == O2D_MEM_DEVICE) return panels_on_points_device(c, np, nx, ny, idx, vs, ss, nt, tx, ty, tu, tv);
+  for (int k = 0; k < 2 * np; ++k)
+    if (idx[k] >= (uint32_t)nnodes) return fail(O2D_ERR_INVALID, "panel node index %u out of range", idx[k]);
+  CU(c->hsrc.reserve(2 * padded_floats(nnodes) + 2 * padded_floats(np)));
+  CU(c->hidx.reserve((size_t)2 * np * sizeof(uint32_t)));
+  CU(c->htgt.reserve(3 * padded_floats(nt)));
+  CU(c->hout.reserve(kMaxOut * padded_floats(nt)));
+  Stager S(c, &c->hsrc), T(c, &c->htgt), O(c, &c->hout);
+  float *dnx = S.take(nnodes), *dny = S.take(nnodes), *dvs = S.take(np), *dss = ss ? S.take(np) : nullptr;
+  float *dtx = T.take(nt), *dty = T.take(nt);
+  float *dtu = O.take(nt), *dtv = O.take(nt);
+  int rc;
+  if ((rc = h2d(c, dnx, nx, nnodes)) || (rc = h2d(c, dny, ny, nnodes)) || (rc = h2d(c, dvs, vs, np)) ||
+      (rc = h2d(c, dtx, tx, nt)) || (rc = h2d(c, dty, ty, nt)) || (rc = h2d(c, dtu, tu, nt)) ||
+      (rc = h2d(c, dtv, tv, nt)))
+    return rc;
+  if (ss && (rc = h2d(c, dss, ss, np))) return rc;
+  CU(cudaMemcpyAsync(c->hidx.p, idx, (size_t)2 * np * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  if ((rc = panels_on_points_device(c, np, dnx, dny, c->hidx.as<uint32_t>(), dvs, dss, nt, dtx, dty, dtu, dtv)))
+    return rc;
+  if ((rc = d2h(c, tu, dtu, nt)) || (rc = d2h(c, tv, dtv, nt))) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  return O2D_OK;
+}
+
+static int points_on_panels_device(o2d_context* c, int ns, const float* sx, const float* sy, const float* ss,
+                                   int np, const float* nx, const float* ny, const uint32_t* idx,
+                                   const float* area, float* pu, float* pv) {
+  if (ns <= 0 || np <= 0) return O2D_OK;
+  const int ntiles = (ns + kTile - 1) / kTile;
+  const int ns_padded = ntiles * kTile;
+  CU(c->packed.reserve((size_t)ns_padded * 16));
+  CU(launch_pack_sources(101, ns, sx, sy, ss, nullptr, c->packed.as<float4>(), ns_padded, c->stream));
+  c->launches++;
+  const int nb = (np + 63) / 64;
+  const int slots = c->sm_count * ptpan_occupancy();
+  const int nchunks = choose_chunks(nb, ntiles, slots, 4096);
+  PtPanArgs a;
+  a.packed_src = c->packed.as<float4>();
+  a.ntiles = ntiles;
+  a.tiles_per_chunk = (ntiles + nchunks - 1) / nchunks;
+  a.nx = nx; a.ny = ny; a.idx = idx; a.area = area; a.np = np; a.pu = pu; a.pv = pv;
+  a.partial = nullptr;
+  if (nchunks > 1) {
+    CU(c->partial.reserve((size_t)nchunks * 2 * (size_t)np * sizeof(double)));
+    a.partial = c->partial.as<double>();
+  }
+  {
+    PairTimer timer(c);
+    CU(launch_points_on_panels(a, nchunks, c->stream));
+    c->launches++;
+    c->pair_launches++;
+  }
+  if (nchunks > 1) {
+    CU(launch_ptpan_combine_geom(a.partial, nchunks, a, c->stream));
+    c->launches++;
+  }
+  return O2D_OK;
+}
+
+extern "C" int o2d_points_on_panels(o2d_context* c, int mem,
+                                    int ns, const float* sx, const float* sy, const float* ss,
+                                    int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                                    const float* area, float* pu, float* pv) {
+  if (int rc = check_common(c, mem)) return rc;
+  if (ns < 0 || np < 0 || nnodes < 0) return fail(O2D_ERR_INVALID, "negative count");
+  if (ns == 0 || np == 0) return O2D_OK;
+  if (!sx || !sy || !ss || !nx || !ny || !idx || !area || !pu || !pv) return fail(O2D_ERR_INVALID, "NULL array");
+  if (mem == O2D_MEM_DEVICE) return points_on_panels_device(c, ns, sx, sy, ss, np, nx, ny, idx, area, pu, pv);
+  for (int k = 0; k < 2 * np; ++k)
+    if (idx[k] >= (uint32_t)nnodes) return fail(O2D_ERR_INVALID, "panel node index %u out of range", idx[k]);
+  CU(c->hsrc.reserve(3 * padded_floats(ns)));
+  CU(c->htgt.reserve(2 * padded_floats(nnodes) + padded_floats(np)));
+  CU(c->hidx.reserve((size_t)2 * np * sizeof(uint32_t)));
+  CU(c->hout.reserve(kMaxOut * padded_floats(np)));
+  Stager S(c, &c->hsrc), T(c, &c->htgt), O(c, &c->hout);
+  float *dsx = S.take(ns), *dsy = S.take(ns), *dss = S.take(ns);
+  float *dnx = T.take(nnodes), *dny = T.take(nnodes), *darea = T.take(np);
+  float *dpu = O.take(np), *dpv = O.take(np);
+  int rc;
+  if ((rc = h2d(c, dsx, sx, ns)) || (rc = h2d(c, dsy, sy, ns)) || (rc = h2d(c, dss, ss, ns)) ||
+      (rc = h2d(c, dnx, nx, nnodes)) || (rc = h2d(c, dny, ny, nnodes)) || (rc = h2d(c, darea, area, np)) ||
+      (rc = h2d(c, dpu, pu, np)) || (rc = h2d(c, dpv, pv, np)))
+    return rc;
+  CU(cudaMemcpyAsync(c->hidx.p, idx, (size_t)2 * np * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  if ((rc = points_on_panels_device(c, ns, dsx, dsy, dss, np, dnx, dny, c->hidx.as<uint32_t>(), darea, dpu, dpv)))
+    return rc;
+  if ((rc = d2h(c, pu, dpu, np)) || (rc = d2h(c, pv, dpv, np))) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  return O2D_OK;
+}
+
+// ---- zero / finalize -------------------------------------------------------------------------------------------
+extern "C" int o2d_zero_vels(o2d_context* c, int mem, int n, float* u, float* v, float* w, float* e) {
+  if (int rc = check_common(c, mem)) return rc;
+  if (n < 0) return fail(O2D_ERR_INVALID, "negative count");
+  if (n == 0) return O2D_OK;
+  if (!u || !v) return fail(O2D_ERR_INVALID, "NULL array");
+  if (mem == O2D_MEM_HOST) {   // host arrays: nothing to launch, this is ElementBase::zero_vels' std::fill
+    std::memset(u, 0, (size_t)n * sizeof(float));
+    std::memset(v, 0, (size_t)n * sizeof(float));
+    if (w) std::memset(w, 0, (size_t)n * sizeof(float));
+    if (e) std::memset(e, 0, (size_t)n * sizeof(float));
+    return O2D_OK;
+  }
+  CU(launch_zero(n, u, v, w, e, c->stream));
+  c->launches++;
+  return O2D_OK;
+}
+
+extern "C" int o2d_finalize_vels(o2d_context* c, int mem, int n, float* u, float* v, float* w, float* e,
+                                 double fsx, double fsy) {
+  if (int rc = check_common(c, mem)) return rc;
+  if (n < 0) return fail(O2D_ERR_INVALID, "negative count");
+  if (n == 0) return O2D_OK;
+  if (!u || !v) return fail(O2D_ERR_INVALID, "NULL array");
+  if (mem == O2D_MEM_DEVICE) {
+    CU(launch_finalize(n, u, v, w, e, fsx, fsy, c->stream));
+    c->launches++;
+    return O2D_OK;
+  }
+  CU(c->hout.reserve(kMaxOut * padded_floats(n)));
+  Stager O(c, &c->hout);
+  float *du = O.take(n), *dv = O.take(n), *dw = w ? O.take(n) : nullptr, *de = e ? O.take(n) : nullptr;
+  int rc;
+  if ((rc = h2d(c, du, u, n)) || (rc = h2d(c, dv, v, n))) return rc;
+  if (w && (rc = h2d(c, dw, w, n))) return rc;
+  if (e && (rc = h2d(c, de, e, n))) return rc;
+  CU(launch_finalize(n, du, dv, dw, de, fsx, fsy, c->stream));
+  c->launches++;
+  if ((rc = d2h(c, u, du, n)) || (rc = d2h(c, v, dv, n))) return rc;
+  if (w && (rc = d2h(c, w, dw, n))) return rc;
+  if (e && (rc = d2h(c, e, de, n))) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  return O2D_OK;
+}
+
+// ---- legacy plugin seam ------------------------------------------------------------------------------------------
+static std::mutex g_legacy_mu;
+static o2d_context* g_legacy_ctx = nullptr;
+static int g_default_core = -1;
+
+static int default_core_locked() {
+  if (g_default_core < 0) {
+    g_default_core = O2D_CORE_V2;   // the reference's shipped #define (src/CoreFunc.h:38)
+    if (const char* e = getenv("O2D_CORE")) {
+      const char* names[] = {"rm", "exp", "wl", "v2", "v3"};
+      for (int i = 0; i < 5; ++i)
+        if (strcasecmp(e, names[i]) == 0) g_default_core = i;
+    }
+  }
+  return g_default_core;
+}
+extern "C" int o2d_set_default_core(int core) {
+  if (core < 0 || core > 4) return fail(O2D_ERR_INVALID, "unknown core %d", core);
+  std::lock_guard<std::mutex> lk(g_legacy_mu);
+  g_default_core = core;
+  return O2D_OK;
+}
+extern "C" int o2d_get_default_core(void) {
+  std::lock_guard<std::mutex> lk(g_legacy_mu);
+  return default_core_locked();
+}
+
+static float legacy_solve(int* ns, const float* sx, const float* sy, const float* ss, const float* sr,
+                          int* nt, const float* tx, const float* ty, const float* tr, float* tu, float* tv) {
+  std::lock_guard<std::mutex> lk(g_legacy_mu);
+  if (!ns || !nt) { fail(O2D_ERR_INVALID, "NULL count"); return -1.0f; }
+  if (!g_legacy_ctx) {
+    int dev = 0;
+    if (const char* e = getenv("O2D_DEVICE")) dev = atoi(e);
+    if (o2d_create(&g_legacy_ctx, dev) != O2D_OK) {
+      fprintf(stderr, "omega2d_b200: %s\n", o2d_last_error());
+      return -1.0f;
+    }
+  }
+  const int core = default_core_locked();
+  int rc = o2d_points_on_points(g_legacy_ctx, core, O2D_VELONLY, O2D_MEM_HOST, *ns, sx, sy, ss, sr, *nt, tx, ty, tr,
+                                tu, tv, nullptr, nullptr, nullptr, nullptr, nullptr);
+  if (rc != O2D_OK) {
+    fprintf(stderr, "omega2d_b200: %s\n", o2d_last_error());
+    return -1.0f;
+  }
+  // flops as the reference's internal branch counts them (src/Influence.h:210,362)
+  const float per_pair = (float)o2d_flops_per_pair(0, core, O2D_VELONLY, tr != nullptr);
+  return (float)(*nt) * (2.0f + per_pair * (float)(*ns));
+}
+
+extern "C" float external_vel_solver_f_(int* ns, const float* sx, const float* sy, const float* ss, const float* sr,
+                                        int* nt, const float* tx, const float* ty, float* tu, float* tv) {
+  return legacy_solve(ns, sx, sy, ss, sr, nt, tx, ty, nullptr, tu, tv);
+}
+extern "C" float external_vel_solver_tr_f_(int* ns, const float* sx, const float* sy, const float* ss, const float* sr,
+                                           int* nt, const float* tx, const float* ty, const float* tr,
+                                           float* tu, float* tv) {
+  return legacy_solve(ns, sx, sy, ss, sr, nt, tx, ty, tr, tu, tv);
+}
+
+// ---- flop accounting (reference counters) ---------------------------------------------------------------------------
+extern "C" int o2d_flops_per_pair(int kind, int core, int results, int blob_targets) {
+  // src/CoreFunc.h flops_tp_nograds / tv_nograds / tp_grads / tv_grads, per core RM EXP WL V2 V3
+  static const int tp_nograds[5] = {3, 7, 5, 6, 8};
+  static const int tv_nograds[5] = {5, 9, 7, 9, 12};
+  static const int tp_grads[5] = {9, 14, 10, 10, 12};
+  static const int tv_grads[5] = {9, 16, 12, 13, 16};
+  if (kind == 1) return 28 + 3 + 8;   // flopsu_1v_0p, scalar flops_usf (src/Kernels.h:292,312)
+  if (kind == 2) return 47;           // flopsu_1vs_0p (src/Kernels.h:362)
+  if (kind == 3) return 13;           // src/InfluenceVort.h:102,119
+  if (kind != 0 || core < 0 || core > 4) return -1;
+  const int b = blob_targets ? 1 : 0;
+  switch (results) {
+    case O2D_VELONLY:     return 10 + (b ? tv_nograds[core] : tp_nograds[core]);   // src/Kernels.h:81,95
+    case O2D_VELANDVORT:  return 19 + (b ? tv_grads[core] : tp_grads[core]);       // src/Kernels.h:139,160
+    case O2D_VELANDSHEAR: return 23 + (b ? tv_grads[core] : tp_grads[core]);       // src/Kernels.h:185,209
+    case O2D_VELANDGRAD:  return 25 + tv_grads[core];                              // src/Kernels.h:112
+  }
+  return -1;
+}
+
+// ---- measurement hooks -------------------------------------------------------------------------------------------------
+extern "C" int o2d_enable_timing(o2d_context* c, int on) {
+  if (!c) return fail(O2D_ERR_INVALID, "ctx is NULL");
+  if (!on && c->timing) { if (int rc = drain_timing(c)) return rc; }
+  c->timing = on != 0;
+  return O2D_OK;
+}
+extern "C" int o2d_reset_counters(o2d_context* c) {
+  if (!c) return fail(O2D_ERR_INVALID, "ctx is NULL");
+  if (int rc = bind_device(c)) return rc;
+  if (int rc = drain_timing(c)) return rc;
+  c->launches = 0; c->pair_launches = 0; c->pair_ms = 0.0;
+  return O2D_OK;
+}
+extern "C" int o2d_get_counters(o2d_context* c, long long* launches, long long* pair_launches, double* pair_ms) {
+  if (!c) return fail(O2D_ERR_INVALID, "ctx is NULL");
+  if (int rc = bind_device(c)) return rc;
+  if (int rc = drain_timing(c)) return rc;
+  if (launches) *launches = c->launches;
+  if (pair_launches) *pair_launches = c->pair_launches;
+  if (pair_ms) *pair_ms = c->pair_ms;
+  return O2D_OK;
+}
+extern "C" int o2d_device_info(o2d_context* c, int* sm_count, int* sm_clock_mhz, double* fp32_peak_tflops) {
+  if (!c) return fail(O2D_ERR_INVALID, "ctx is NULL");
+  if (sm_count) *sm_count = c->sm_count;
+  if (sm_clock_mhz) *sm_clock_mhz = c->sm_clock_khz / 1000;
+  if (fp32_peak_tflops) *fp32_peak_tflops = (double)c->sm_count * 128.0 * 2.0 * (double)c->sm_clock_khz * 1e3 / 1e12;
+  return O2D_OK;
+}
+extern "C" int o2d_measure_fp32_peak(o2d_context* c, int packed, double* tflops) {
+  if (!c || !tflops) return fail(O2D_ERR_INVALID, "NULL argument");
+  if (int rc = bind_device(c)) return rc;
+  CU(c->partial.reserve(256));
+  float* sink = c->partial.as<float>();
+  const int blocks = c->sm_count * 8, threads = 256, iters = 4096;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  CU(run_fp32_microbench(packed, blocks, threads, 64, sink, c->stream));   // warm-up
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CU(cudaEventRecord(e0, c->stream));
+    CU(run_fp32_microbench(packed, blocks, threads, iters, sink, c->stream));
+    CU(cudaEventRecord(e1, c->stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.0f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * (double)kMicrobenchFmaPerIter * iters * (double)blocks * threads;
+    best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  c->launches += 6;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *tflops = best;
+  return O2D_OK;
+}
+
+// ---- multi-GPU ------------------------------------------------------------------------------------------------------------
+extern "C" int o2d_comm_unique_id(void* id128) {
+  if (!id128) return fail(O2D_ERR_INVALID, "id buffer is NULL");
+  std::lock_guard<std::mutex> lk(g_nccl_mu);
+  if (!g_nccl.load()) return fail(O2D_ERR_COMM, "cannot load libnccl.so.2: %s", dlerror());
+  NcclUid uid;
+  int r = g_nccl.GetUniqueId(&uid);
+  if (r != 0) return fail(O2D_ERR_COMM, "ncclGetUniqueId: %s", g_nccl.GetErrorString(r));
+  static_assert(sizeof(NcclUid) == O2D_UNIQUE_ID_BYTES, "unique id size");
+  memcpy(id128, &uid, sizeof(uid));
+  return O2D_OK;
+}
+
+extern "C" int o2d_comm_init(o2d_context* c, int nranks, int rank, const void* id128) {
+  if (!c || !id128) return fail(O2D_ERR_INVALID, "NULL argument");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(O2D_ERR_INVALID, "bad rank %d of %d", rank, nranks);
+  if (int rc = bind_device(c)) return rc;
+  {
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (!g_nccl.load()) return fail(O2D_ERR_COMM, "cannot load libnccl.so.2: %s", dlerror());
+  }
+  if (c->comm) o2d_comm_destroy(c);
+  NcclUid uid;
+  memcpy(&uid, id128, sizeof(uid));
+  int r = g_nccl.CommInitRank(&c->comm, nranks, uid, rank);
+  if (r != 0) { c->comm = nullptr; return fail(O2D_ERR_COMM, "ncclCommInitRank: %s", g_nccl.GetErrorString(r)); }
+  c->nranks = nranks;
+  c->rank = rank;
+  return O2D_OK;
+}
+
+extern "C" int o2d_comm_destroy(o2d_context* c) {
+  if (!c) return O2D_OK;
+  if (c->comm) {
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->comm_stream);
+    g_nccl.CommDestroy(c->comm);
+    c->comm = nullptr;
+  }
+  c->nranks = 1;
+  c->rank = 0;
+  return O2D_OK;
+}
+
+static int pp_sharded_device(o2d_context* c, int core, int res, int ns_local, int ns_block,
+                             const float* sx, const float* sy, const float* ss, const float* sr,
+                             int nt, const float* tx, const float* ty, const float* tr, const OutPtrs& out) {
+  const int P = c->nranks;
+  const int bt = (ns_block + kTile - 1) / kTile;          // tiles per rank block
+  const size_t block_bytes = (size_t)bt * kTile * 16;
+  CU(c->packed_all.reserve(block_bytes * P));
+  float4* all = c->packed_all.as<float4>();
+  float4* mine = all + (size_t)c->rank * bt * kTile;
+  // pack this rank's block in place inside the gather buffer (padding = zero-strength copies)
+  // (an empty block packs as zero-strength unit-radius particles at the origin)
+  CU(launch_pack_sources(core, ns_local, sx, sy, ss, sr, mine, bt * kTile, c->stream));
+  c->launches++;
+  CU(cudaEventRecord(c->ev_pack, c->stream));
+  // all-gather on the comm stream while the local block is being summed
+  if (P > 1) {
+    CU(cudaStreamWaitEvent(c->comm_stream, c->ev_pack, 0));
+    int r = g_nccl.AllGather(mine, all, block_bytes, kNcclChar, c->comm, c->comm_stream);
+    if (r != 0) return fail(O2D_ERR_COMM, "ncclAllGather: %s", g_nccl.GetErrorString(r));
+    CU(cudaEventRecord(c->ev_gather, c->comm_stream));
+  }
+  if (nt <= 0) {
+    if (P > 1) CU(cudaStreamWaitEvent(c->stream, c->ev_gather, 0));
+    return O2D_OK;
+  }
+  const int R = res_targets_per_thread(res);
+  const int nb = (nt + kThreads * R - 1) / (kThreads * R);
+  const int slots = c->sm_count * pp_occupancy(core, res);
+  // chunk the local block and the remote range separately; partial sums from both are combined
+  const int nc_local = choose_chunks(nb, bt, slots, 256);
+  const int rt = bt * (P - 1);
+  const int nc_remote = rt > 0 ? choose_chunks(nb, rt, slots, 256) : 0;
+  const int nchunks = nc_local + nc_remote;
+  CU(c->partial.reserve((size_t)nchunks * res_ncomp(res) * (size_t)nt * sizeof(double)));
+  double* partial = c->partial.as<double>();
+  int cursor = 0;
+  {
+    PairTimer timer(c);
+    int rc = pp_run_packed(c, core, res, all, c->rank * bt, (c->rank + 1) * bt, INT_MAX, 0, tx, ty, tr, nt, out,
+                           &cursor, nc_local, partial);
+    if (rc) return rc;
+    if (rt > 0) {
+      CU(cudaStreamWaitEvent(c->stream, c->ev_gather, 0));
+      // logical tiles [0, rt) hop over this rank's own block
+      rc = pp_run_packed(c, core, res, all, 0, rt, c->rank * bt, bt, tx, ty, tr, nt, out, &cursor, nc_remote, partial);
+      if (rc) return rc;
+    }
+  }
+  CU(launch_pp_combine(res, partial, nchunks, nt, out, c->stream));
+  c->launches++;
+  return O2D_OK;
+}
+
+extern "C" int o2d_points_on_points_sharded(o2d_context* c, int core, int results, int mem,
+                                            int ns_local, int ns_block,
+                                            const float* sx, const float* sy, const float* ss, const float* sr,
+                                            int nt, const float* tx, const float* ty, const float* tr,
+                                            float* tu, float* tv, float* tq,
+                                            float* tux, float* tvx, float* tuy, float* tvy) {
+  if (int rc = check_common(c, mem)) return rc;
+  if (c->nranks > 1 && !c->comm) return fail(O2D_ERR_COMM, "communicator not initialised (o2d_comm_init)");
+  if (core < 0 || core > 4) return fail(O2D_ERR_INVALID, "unknown core %d", core);
+  if (results == O2D_PSIONLY) return fail(O2D_ERR_UNSUPPORTED, "streamfunction results are not supported");
+  const int res = res_from_results(results);
+  if (res < 0) return fail(O2D_ERR_INVALID, "unknown results type %d", results);
+  if (ns_local < 0 || nt < 0 || ns_block <= 0 || ns_local > ns_block)
+    return fail(O2D_ERR_INVALID, "bad counts ns_local=%d ns_block=%d nt=%d", ns_local, ns_block, nt);
+  if (ns_local > 0 && (!sx || !sy || !ss || !sr)) return fail(O2D_ERR_INVALID, "NULL source array");
+  if (nt > 0 && (!tx || !ty)) return fail(O2D_ERR_INVALID, "NULL target array");
+  float* outs[kMaxOut] = {nullptr};
+  int nout = 0;
+  if (nt > 0) {
+    nout = collect_outputs(res, tu, tv, tq, tux, tvx, tuy, tvy, outs);
+    if (nout < 0) return nout;
+  }
+  OutPtrs o{};
+  if (mem == O2D_MEM_DEVICE) {
+    for (int k = 0; k < nout; ++k) o.p[k] = outs[k];
+    return pp_sharded_device(c, core, res, ns_local, ns_block, sx, sy, ss, sr, nt, tx, ty, tr, o);
+  }
+  CU(c->hsrc.reserve(4 * padded_floats(ns_local) + 256));
+  CU(c->htgt.reserve(3 * padded_floats(nt) + 256));
+  CU(c->hout.reserve(kMaxOut * padded_floats(nt) + 256));
+  Stager S(c, &c->hsrc), T(c, &c->htgt), O(c, &c->hout);
+  float *dsx = S.take(ns_local), *dsy = S.take(ns_local), *dss = S.take(ns_local), *dsr = S.take(ns_local);
+  float *dtx = T.take(nt), *dty = T.take(nt), *dtr = tr ? T.take(nt) : nullptr;
+  int rc;
+  if ((rc = h2d(c, dsx, sx, ns_local)) || (rc = h2d(c, dsy, sy, ns_local)) || (rc = h2d(c, dss, ss, ns_local)) ||
+      (rc = h2d(c, dsr, sr, ns_local)) || (rc = h2d(c, dtx, tx, nt)) || (rc = h2d(c, dty, ty, nt)))
+    return rc;
+  if (tr && (rc = h2d(c, dtr, tr, nt))) return rc;
+  for (int k = 0; k < nout; ++k) {
+    o.p[k] = O.take(nt);
+    if ((rc = h2d(c, o.p[k], outs[k], nt))) return rc;
+  }
+  if ((rc = pp_sharded_device(c, core, res, ns_local, ns_block, dsx, dsy, dss, dsr, nt, dtx, dty, dtr, o))) return rc;
+  for (int k = 0; k < nout; ++k)
+    if ((rc = d2h(c, outs[k], o.p[k], nt))) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  return O2D_OK;
+}

@@ -1,0 +1,145 @@
+// o2d_device.cuh -- device-side building blocks shared by the pair-sum kernels (sm_100a only).
+//
+//  * MUFU wrappers (rcp/rsqrt/ex2/lg2 .approx.ftz): one SFU instruction each, <= 2^-22 relative
+//    error, two orders of magnitude inside the 1e-5 parity tolerance.
+//  * Blackwell packed-FP32 helpers: FADD2/FMUL2/FFMA2 process two independent float lanes per
+//    issue slot.  A lane pair here is always TWO SOURCES against ONE target.
+//  * TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers used to stage source
+//    tiles into shared memory.
+//  * The five core functions of reference src/CoreFunc.h, written on packed lanes.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "o2d_internal.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "omega2d_b200 kernels are written for sm_100a only"
+#endif
+
+namespace o2d {
+
+// ---- SFU -----------------------------------------------------------------------------------
+__device__ __forceinline__ float mufu_rcp(float x)   { float r; asm("rcp.approx.ftz.f32 %0, %1;"   : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float mufu_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float mufu_ex2(float x)   { float r; asm("ex2.approx.ftz.f32 %0, %1;"   : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float mufu_lg2(float x)   { float r; asm("lg2.approx.ftz.f32 %0, %1;"   : "=f"(r) : "f"(x)); return r; }
+
+// ---- packed FP32 (FADD2 / FMUL2 / FFMA2) ------------------------------------------------------
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2(float a)          { return make_float2(a, a); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b)           { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b)           { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 rcp2(float2 a)   { return make_float2(mufu_rcp(a.x), mufu_rcp(a.y)); }
+__device__ __forceinline__ float2 rsqrt2(float2 a) { return make_float2(mufu_rsqrt(a.x), mufu_rsqrt(a.y)); }
+
+// ---- mbarrier + TMA bulk copy ----------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy through the TMA unit; completion is signalled on `bar`
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---- radius terms ----------------------------------------------------------------------------
+// Per-element radius term the cores add to the distance term: r^2 for RM/EXP/WL, r^4 for V2,
+// r^6 for V3, formed with the reference's own float products (s2 = sr*sr; s2*s2; s2*s2*s2,
+// reference src/CoreFunc.h:48,147,199,247-249,292-294).  Inert targets use 0, which makes the
+// blob-target ("0b") expression equal the inert-target ("0p") one.
+template <int CORE>
+__host__ __device__ __forceinline__ float radius_term(float r) {
+  const float r2 = r * r;
+  if (CORE == CORE_V2) return r2 * r2;
+  if (CORE == CORE_V3) return r2 * r2 * r2;
+  return r2;
+}
+
+// ---- core functions on packed lanes ----------------------------------------------------------
+// Inputs per lane: dx,dy = target - source, rho = source radius term, tau = target radius term.
+// Outputs: K (the reference's core_func return / *r2), d2 = dx^2+dy^2 (only valid when GRAD or
+// when the core needs it), and, when GRAD, B (the reference's *bbb).
+// Strength multiplication is left to the caller.
+template <int CORE, bool GRAD>
+__device__ __forceinline__ void core_eval(float2 dx, float2 dy, float2 rho, float2 tau,
+                                          float2& K, float2& B, float2& d2) {
+  if (CORE == CORE_RM) {
+    // src/CoreFunc.h:54-58,74-80: K = 1/(d2 + sr^2 + tr^2), bbb = -2 K^2
+    float2 q;
+    if (GRAD) {
+      d2 = fma2(dy, dy, mul2(dx, dx));
+      q = add2(add2(d2, tau), rho);
+    } else {
+      q = add2(fma2(dy, dy, fma2(dx, dx, tau)), rho);   // 3 FP32 ops, no separate d2
+    }
+    K = rcp2(q);
+    if (GRAD) B = mul2(mul2(f2(-2.0f), K), K);
+  } else if (CORE == CORE_V2) {
+    // src/CoreFunc.h:245-250,266-273: K = rsqrt(d2^2 + sr^4 + tr^4), bbb = -2 K^3 d2
+    d2 = fma2(dy, dy, mul2(dx, dx));
+    const float2 q = add2(fma2(d2, d2, tau), rho);
+    K = rsqrt2(q);
+    if (GRAD) B = mul2(mul2(mul2(f2(-2.0f), K), mul2(K, K)), d2);
+  } else if (CORE == CORE_V3) {
+    // src/CoreFunc.h:290-295,312-320: K = cbrt(d2^3 + sr^6 + tr^6)^-1, bbb = -2 d2^2 K / (d2^3+..)
+    d2 = fma2(dy, dy, mul2(dx, dx));
+    const float2 q = add2(fma2(mul2(d2, d2), d2, tau), rho);
+    // q^(-1/3) = 2^(-lg2(q)/3), then one Newton step  k <- k + k (1 - q k^3)/3  on the FMA pipe
+    const float2 k = make_float2(mufu_ex2(-0.33333334f * mufu_lg2(q.x)), mufu_ex2(-0.33333334f * mufu_lg2(q.y)));
+    const float2 k3 = mul2(mul2(k, k), k);
+    const float2 e = fma2(mul2(f2(-1.0f), q), k3, f2(1.0f));
+    K = fma2(mul2(k, f2(0.33333334f)), e, k);
+    // q == 0 (coincident zero-radius pair) gives inf*0 above; the reference returns inf there
+    if (q.x == 0.0f) K.x = __int_as_float(0x7f800000);
+    if (q.y == 0.0f) K.y = __int_as_float(0x7f800000);
+    if (GRAD) B = mul2(mul2(mul2(f2(-2.0f), mul2(d2, d2)), K), rcp2(q));
+  } else if (CORE == CORE_WL) {
+    // src/CoreFunc.h:197-202,220-228: s2 = sr^2+tr^2, D = d2+s2, K = (D+s2)/D^2 = r + s2 r^2
+    // with r = 1/D;  bbb = (2 - 4 K D)/D^2 = (2 - 4 K D) r^2
+    const float2 s2 = add2(rho, tau);
+    if (GRAD) d2 = fma2(dy, dy, mul2(dx, dx));
+    const float2 D = GRAD ? add2(d2, s2) : fma2(dy, dy, fma2(dx, dx, s2));
+    const float2 r = rcp2(D);
+    K = fma2(mul2(s2, r), r, r);
+    if (GRAD) B = mul2(fma2(mul2(f2(-4.0f), K), D, f2(2.0f)), mul2(r, r));
+  } else {  // CORE_EXP
+    // src/CoreFunc.h:118-130,144-150,170-179: ood2 = 1/d2, corefac = 1/(sr^2+tr^2),
+    // reld2 = corefac/ood2; K = ood2 (reld2>16) | corefac (reld2<0.001) | ood2 (1-exp(-reld2));
+    // bbb = -2 K ood2 + 2 corefac ood2 exp(-reld2)   (NaN at d2 == 0, as in the reference)
+    d2 = fma2(dy, dy, mul2(dx, dx));
+    const float2 ood2 = rcp2(d2);
+    const float2 corefac = rcp2(add2(rho, tau));
+    const float2 reld2 = mul2(d2, corefac);
+    const float kLog2e = 1.4426950408889634f;
+    const float2 ex = make_float2(mufu_ex2(-kLog2e * reld2.x), mufu_ex2(-kLog2e * reld2.y));
+    const float2 mid = mul2(ood2, fma2(ex, f2(-1.0f), f2(1.0f)));
+    K.x = reld2.x > 16.0f ? ood2.x : (reld2.x < 0.001f ? corefac.x : mid.x);
+    K.y = reld2.y > 16.0f ? ood2.y : (reld2.y < 0.001f ? corefac.y : mid.y);
+    if (GRAD) {
+      const float2 t = mul2(mul2(f2(2.0f), corefac), mul2(ood2, ex));
+      B = fma2(mul2(f2(-2.0f), K), ood2, t);
+    }
+  }
+}
+
+}  // namespace o2d

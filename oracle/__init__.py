@@ -1,0 +1,268 @@
+"""oracle -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+ctypes front-ends for the two CPU checkers of the Omega2D Biot-Savart hot path:
+
+* ``port``  -- ``oracle/libo2d_oracle.so``, the plain-C restatement in ``o2d_oracle.c``
+  (all five cores selectable at run time);
+* ``ref(core)`` -- ``oracle/_ref/libo2dref_<core>.so``, the UNMODIFIED reference templates
+  (``points_affect_points<float,double>`` etc., reference src/Influence.h) compiled by
+  ``oracle/build_ref.sh``; one library per core because the reference picks the core with a
+  ``#define`` (reference src/CoreFunc.h:35-39).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / reference
+arm may import this package.  The product (``omega2d_b200``) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+CORES = ("rm", "exp", "wl", "v2", "v3")
+CORE_ID = {name: i for i, name in enumerate(CORES)}
+# reference results_t values (reference src/ResultsType.h:25-31)
+VELONLY, VELANDGRAD, PSIONLY, VELANDVORT, VELANDSHEAR = 1, 2, 3, 4, 5
+
+_fp = C.POINTER(C.c_float)
+_up = C.POINTER(C.c_uint32)
+
+
+def _f(a):
+    if a is None:
+        return None
+    assert a.dtype == np.float32 and a.flags.c_contiguous
+    return a.ctypes.data_as(_fp)
+
+
+def _u(a):
+    assert a.dtype == np.uint32 and a.flags.c_contiguous
+    return a.ctypes.data_as(_up)
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+def build_port() -> str:
+    """(Re)build the C restatement if missing or stale; returns the library path."""
+    so = os.path.join(HERE, "libo2d_oracle.so")
+    src = os.path.join(HERE, "o2d_oracle.c")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", HERE, "-s"], check=True)
+    return so
+
+
+def build_ref(reference: str = "/root/reference") -> bool:
+    """Build oracle/_ref from the reference sources when they are present.  Returns True
+    when all five libraries exist afterwards (prebuilt ones count)."""
+    if os.path.isdir(os.path.join(reference, "src")):
+        drv = os.path.join(HERE, "ref_driver.cpp")
+        stale = any(
+            not os.path.exists(ref_path(c)) or os.path.getmtime(ref_path(c)) < os.path.getmtime(drv)
+            for c in CORES
+        )
+        if stale:
+            env = dict(os.environ, O2D_REFERENCE=reference)
+            subprocess.run([os.path.join(HERE, "build_ref.sh")], check=True, env=env)
+    return have_ref()
+
+
+def ref_path(core: str) -> str:
+    return os.path.join(HERE, "_ref", f"libo2dref_{core}.so")
+
+
+def have_ref() -> bool:
+    return all(os.path.exists(ref_path(c)) for c in CORES)
+
+
+class Port:
+    """The plain-C restatement (o2d_oracle.c)."""
+
+    kind = "port"
+
+    def __init__(self):
+        self.lib = C.CDLL(build_port())
+
+    def flops(self, core: str, which: int, has_tr: bool) -> int:
+        return int(self.lib.o2d_oracle_flops(CORE_ID[core], which, int(has_tr)))
+
+    def points_on_points(self, core, results, sx, sy, ss, sr, tx, ty, tr=None, tu=None, tv=None, tq=None):
+        sx, sy, ss, sr, tx, ty, tr = map(_f32, (sx, sy, ss, sr, tx, ty, tr))
+        nt = tx.size
+        tu = np.zeros(nt, np.float32) if tu is None else np.array(tu, np.float32)
+        tv = np.zeros(nt, np.float32) if tv is None else np.array(tv, np.float32)
+        want_q = results in (VELANDVORT, VELANDSHEAR)
+        if want_q:
+            tq = np.zeros(nt, np.float32) if tq is None else np.array(tq, np.float32)
+        rc = self.lib.o2d_oracle_points_on_points(
+            CORE_ID[core], int(results), int(sx.size), _f(sx), _f(sy), _f(ss), _f(sr),
+            int(nt), _f(tx), _f(ty), _f(tr), _f(tu), _f(tv), _f(tq) if want_q else None)
+        if rc != 0:
+            raise ValueError(f"oracle rejected results type {results}")
+        return (tu, tv, tq) if want_q else (tu, tv)
+
+    def points_on_points_grad(self, core, sx, sy, ss, sr, tx, ty, tr=None, skip_self=False):
+        sx, sy, ss, sr, tx, ty, tr = map(_f32, (sx, sy, ss, sr, tx, ty, tr))
+        nt = tx.size
+        out = [np.zeros(nt, np.float32) for _ in range(6)]
+        rc = self.lib.o2d_oracle_points_on_points_grad(
+            CORE_ID[core], int(sx.size), _f(sx), _f(sy), _f(ss), _f(sr),
+            int(nt), _f(tx), _f(ty), _f(tr), *[_f(o) for o in out], int(skip_self))
+        assert rc == 0
+        return tuple(out)  # u, v, ux, vx, uy, vy
+
+    def panels_on_points(self, nx, ny, idx, vs, ss, tx, ty, tu=None, tv=None):
+        nx, ny, vs, ss, tx, ty = map(_f32, (nx, ny, vs, ss, tx, ty))
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        nt = tx.size
+        tu = np.zeros(nt, np.float32) if tu is None else np.array(tu, np.float32)
+        tv = np.zeros(nt, np.float32) if tv is None else np.array(tv, np.float32)
+        rc = self.lib.o2d_oracle_panels_on_points(
+            int(vs.size), int(nx.size), _f(nx), _f(ny), _u(idx), _f(vs), _f(ss),
+            int(nt), _f(tx), _f(ty), _f(tu), _f(tv))
+        assert rc == 0
+        return tu, tv
+
+    def panel_areas(self, nx, ny, idx):
+        nx, ny = map(_f32, (nx, ny))
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        area = np.zeros(idx.size // 2, np.float32)
+        self.lib.o2d_oracle_panel_areas(int(area.size), _f(nx), _f(ny), _u(idx), _f(area))
+        return area
+
+    def points_on_panels(self, sx, sy, ss, nx, ny, idx, area=None, pu=None, pv=None):
+        sx, sy, ss, nx, ny = map(_f32, (sx, sy, ss, nx, ny))
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        npan = idx.size // 2
+        area = self.panel_areas(nx, ny, idx) if area is None else _f32(area)
+        pu = np.zeros(npan, np.float32) if pu is None else np.array(pu, np.float32)
+        pv = np.zeros(npan, np.float32) if pv is None else np.array(pv, np.float32)
+        rc = self.lib.o2d_oracle_points_on_panels(
+            int(sx.size), _f(sx), _f(sy), _f(ss), int(npan), int(nx.size), _f(nx), _f(ny), _u(idx),
+            _f(area), _f(pu), _f(pv))
+        assert rc == 0
+        return pu, pv
+
+    def points_vorticity(self, sx, sy, ss, sr, tx, ty, tw=None):
+        sx, sy, ss, sr, tx, ty = map(_f32, (sx, sy, ss, sr, tx, ty))
+        nt = tx.size
+        tw = np.zeros(nt, np.float32) if tw is None else np.array(tw, np.float32)
+        rc = self.lib.o2d_oracle_points_vorticity(
+            int(sx.size), _f(sx), _f(sy), _f(ss), _f(sr), int(nt), _f(tx), _f(ty), _f(tw))
+        assert rc == 0
+        return tw
+
+    def finalize_vels(self, u, v, w=None, e=None, fs=(0.0, 0.0)):
+        u, v = np.array(u, np.float32), np.array(v, np.float32)
+        w = None if w is None else np.array(w, np.float32)
+        e = None if e is None else np.array(e, np.float32)
+        self.lib.o2d_oracle_finalize_vels.argtypes = [C.c_int, _fp, _fp, _fp, _fp, C.c_double, C.c_double]
+        self.lib.o2d_oracle_finalize_vels(int(u.size), _f(u), _f(v), _f(w), _f(e), float(fs[0]), float(fs[1]))
+        return u, v, w, e
+
+
+class Ref:
+    """The unmodified reference templates for ONE core (oracle/_ref/libo2dref_<core>.so)."""
+
+    kind = "reference"
+
+    def __init__(self, core: str):
+        self.core = core
+        self.lib = C.CDLL(ref_path(core))
+        assert self.lib.o2dref_core_id() == CORE_ID[core]
+
+    def flops(self, which: int) -> int:
+        return int(self.lib.o2dref_flops(which))
+
+    def points_on_points(self, results, sx, sy, ss, sr, tx, ty, tr=None, tu=None, tv=None, tq=None):
+        sx, sy, ss, sr, tx, ty, tr = map(_f32, (sx, sy, ss, sr, tx, ty, tr))
+        nt = tx.size
+        tu = np.zeros(nt, np.float32) if tu is None else np.array(tu, np.float32)
+        tv = np.zeros(nt, np.float32) if tv is None else np.array(tv, np.float32)
+        want_q = results in (VELANDVORT, VELANDSHEAR)
+        if want_q:
+            tq = np.zeros(nt, np.float32) if tq is None else np.array(tq, np.float32)
+        rc = self.lib.o2dref_points_on_points(
+            int(results), int(sx.size), _f(sx), _f(sy), _f(ss), _f(sr),
+            int(nt), _f(tx), _f(ty), _f(tr), _f(tu), _f(tv), _f(tq) if want_q else None)
+        if rc != 0:
+            raise ValueError(f"reference rejects results type {results}")
+        return (tu, tv, tq) if want_q else (tu, tv)
+
+    def points_on_points_grad(self, sx, sy, ss, sr, tx, ty, tr, skip_self=False):
+        sx, sy, ss, sr, tx, ty, tr = map(_f32, (sx, sy, ss, sr, tx, ty, tr))
+        nt = tx.size
+        out = [np.zeros(nt, np.float32) for _ in range(6)]
+        rc = self.lib.o2dref_points_on_points_grad(
+            int(sx.size), _f(sx), _f(sy), _f(ss), _f(sr),
+            int(nt), _f(tx), _f(ty), _f(tr), *[_f(o) for o in out], int(skip_self))
+        assert rc == 0
+        return tuple(out)
+
+    def panels_on_points(self, nx, ny, idx, vs, ss, tx, ty, tu=None, tv=None):
+        nx, ny, vs, ss, tx, ty = map(_f32, (nx, ny, vs, ss, tx, ty))
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        nt = tx.size
+        tu = np.zeros(nt, np.float32) if tu is None else np.array(tu, np.float32)
+        tv = np.zeros(nt, np.float32) if tv is None else np.array(tv, np.float32)
+        if ss is None:
+            rc = self.lib.o2dref_panels_on_points_vortex(
+                int(vs.size), int(nx.size), _f(nx), _f(ny), _u(idx), _f(vs),
+                int(nt), _f(tx), _f(ty), _f(tu), _f(tv))
+        else:
+            rc = self.lib.o2dref_panels_on_points(
+                int(vs.size), int(nx.size), _f(nx), _f(ny), _u(idx), _f(vs), _f(ss),
+                int(nt), _f(tx), _f(ty), _f(tu), _f(tv))
+        assert rc == 0
+        return tu, tv
+
+    def points_on_panels(self, sx, sy, ss, nx, ny, idx, pu=None, pv=None):
+        sx, sy, ss, nx, ny = map(_f32, (sx, sy, ss, nx, ny))
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        npan = idx.size // 2
+        pu = np.zeros(npan, np.float32) if pu is None else np.array(pu, np.float32)
+        pv = np.zeros(npan, np.float32) if pv is None else np.array(pv, np.float32)
+        area = np.zeros(npan, np.float32)
+        rc = self.lib.o2dref_points_on_panels(
+            int(sx.size), _f(sx), _f(sy), _f(ss), int(npan), int(nx.size), _f(nx), _f(ny), _u(idx),
+            _f(pu), _f(pv), _f(area))
+        assert rc == 0
+        return pu, pv, area
+
+    def points_vorticity(self, sx, sy, ss, sr, tx, ty, tw=None):
+        sx, sy, ss, sr, tx, ty = map(_f32, (sx, sy, ss, sr, tx, ty))
+        nt = tx.size
+        tw = np.zeros(nt, np.float32) if tw is None else np.array(tw, np.float32)
+        rc = self.lib.o2dref_points_vorticity(
+            int(sx.size), _f(sx), _f(sy), _f(ss), _f(sr), int(nt), _f(tx), _f(ty), _f(tw))
+        assert rc == 0
+        return tw
+
+    def finalize_vels(self, u, v, w=None, e=None, fs=(0.0, 0.0)):
+        u, v = np.array(u, np.float32), np.array(v, np.float32)
+        w = None if w is None else np.array(w, np.float32)
+        e = None if e is None else np.array(e, np.float32)
+        self.lib.o2dref_finalize_vels.argtypes = [C.c_int, _fp, _fp, _fp, _fp, C.c_double, C.c_double]
+        self.lib.o2dref_finalize_vels(int(u.size), _f(u), _f(v), _f(w), _f(e), float(fs[0]), float(fs[1]))
+        return u, v, w, e
+
+
+_port = None
+_refs = {}
+
+
+def port() -> Port:
+    global _port
+    if _port is None:
+        _port = Port()
+    return _port
+
+
+def ref(core: str) -> Ref:
+    if core not in _refs:
+        _refs[core] = Ref(core)
+    return _refs[core]

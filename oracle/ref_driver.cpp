@@ -1,0 +1,258 @@
+// oracle/ref_driver.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// Thin extern "C" shim around the UNMODIFIED Omega2D reference headers, built by
+// oracle/build_ref.sh into oracle/_ref/libo2dref_<core>.so (git-ignored).  One
+// shared object per core function because the reference selects the core with
+// an unguarded #define (reference src/CoreFunc.h:35-39).
+//
+// Every entry point builds the reference's own containers (Points<float>,
+// Surfaces<float>) from raw SoA arrays, calls the reference's own templates
+// with <S=float, A=double> (the USE_VC-off configuration, reference
+// src/Simulation.h:44-50), and copies the results back with the reference's
+// accumulate ("+=") semantics.  Nothing here restates reference arithmetic
+// except the two loops the reference never wraps itself:
+//   * velocity+gradient: kernelug_0v_0b is never called by any reference loop
+//     (SURVEY F5), so the points_affect_points loop nest (src/Influence.h:347-361)
+//     is restated around the reference's own kernelug_0v_0b (src/Kernels.h:112-133);
+//   * vortex-only panels: Surfaces always engages the source strengths
+//     (src/Surfaces.h:87-92), so the have_source_strengths==false branch of
+//     panels_affect_points (src/Influence.h:576-594) is restated around the
+//     reference's own kernelu_1v_0p (src/Kernels.h:312-354).
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference
+// arm may load this library.
+
+// Collection.h must come first: Influence.h is not self-contained.
+#include "Collection.h"
+#include "Influence.h"
+#include "InfluenceVort.h"
+
+#include <cstdio>
+#include <cstring>
+#include <fcntl.h>
+#include <iostream>
+#include <unistd.h>
+#include <vector>
+
+namespace {
+
+// The reference narrates on std::cout and printf from inside the hot functions
+// (src/Influence.h:59,115,412-415).  Silence fd 1 for the duration of a call so
+// that a harness printing one JSON line on stdout stays clean.
+struct StdoutMute {
+  int saved = -1;
+  std::streambuf* cout_buf = nullptr;
+  StdoutMute() {
+    fflush(stdout);
+    std::cout.flush();
+    saved = dup(1);
+    int devnull = open("/dev/null", O_WRONLY);
+    if (devnull >= 0) { dup2(devnull, 1); close(devnull); }
+  }
+  ~StdoutMute() {
+    fflush(stdout);
+    std::cout.flush();
+    if (saved >= 0) { dup2(saved, 1); close(saved); }
+  }
+};
+
+Points<float> make_points(int n, const float* x, const float* y, const float* s, const float* r) {
+  // ElementPacket carries interleaved xy (src/ElementPacket.h:166-171)
+  std::vector<float> px(2 * (size_t)n);
+  for (int i = 0; i < n; ++i) { px[2*i] = x[i]; px[2*i+1] = y[i]; }
+  if (s == nullptr) {
+    // inert field points: no strength, no radius (src/Points.h:93-95)
+    ElementPacket<float> pk(px, std::vector<Int>(), std::vector<float>(), (size_t)n, 0);
+    return Points<float>(pk, inert, fixed, nullptr, 0.0f);
+  }
+  std::vector<float> val(s, s + n);
+  ElementPacket<float> pk(px, std::vector<Int>(), val, (size_t)n, 0);
+  Points<float> pts(pk, active, lagrangian, nullptr, 1.0f);
+  if (r != nullptr) {
+    Vector<float>& rad = pts.get_rad();
+    for (int i = 0; i < n; ++i) rad[i] = r[i];
+  }
+  return pts;
+}
+
+Surfaces<float> make_surfaces(int np, int nnodes, const float* nx, const float* ny,
+                              const uint32_t* idx, const float* vs, const float* ss) {
+  std::vector<float> px(2 * (size_t)nnodes);
+  for (int i = 0; i < nnodes; ++i) { px[2*i] = nx[i]; px[2*i+1] = ny[i]; }
+  std::vector<Int> pidx(idx, idx + 2 * (size_t)np);
+  std::vector<float> val(2 * (size_t)np);
+  for (int i = 0; i < np; ++i) { val[2*i] = vs ? vs[i] : 0.0f; val[2*i+1] = ss ? ss[i] : 0.0f; }
+  ElementPacket<float> pk(px, pidx, val, (size_t)np, 1);
+  return Surfaces<float>(pk, active, fixed, nullptr);
+}
+
+}  // namespace
+
+extern "C" {
+
+// which core this object was built with: 0 RM, 1 EXP, 2 WL, 3 V2, 4 V3
+int o2dref_core_id() {
+#if defined(USE_RM_KERNEL)
+  return 0;
+#elif defined(USE_EXPONENTIAL_KERNEL)
+  return 1;
+#elif defined(USE_WL_KERNEL)
+  return 2;
+#elif defined(USE_V2_KERNEL)
+  return 3;
+#elif defined(USE_V3_KERNEL)
+  return 4;
+#else
+  return -1;
+#endif
+}
+
+// reference per-pair flop counters (src/Kernels.h flops*_...(), src/CoreFunc.h flops_t*_*())
+// which: 0 u_0p, 1 u_0b, 2 uw_0p, 3 uw_0b, 4 ue_0p, 5 ue_0b, 6 ug_0b, 7 u_1v_0p, 8 u_1vs_0p
+int o2dref_flops(int which) {
+  switch (which) {
+    case 0: return (int)flopsu_0v_0p<float,double>();
+    case 1: return (int)flopsu_0v_0b<float,double>();
+    case 2: return (int)flopsuw_0v_0p<float,double>();
+    case 3: return (int)flopsuw_0v_0b<float,double>();
+    case 4: return (int)flopsue_0v_0p<float,double>();
+    case 5: return (int)flopsue_0v_0b<float,double>();
+    case 6: return (int)flopsug_0v_0b<float,double>();
+    case 7: return (int)flopsu_1v_0p<float,double>();
+    case 8: return (int)flopsu_1vs_0p<float,double>();
+  }
+  return -1;
+}
+
+// reference points_affect_points<float,double> (src/Influence.h:56-416).
+// results_type uses the reference's results_t values (src/ResultsType.h:25-31):
+// 1 velonly, 4 velandvort, 5 velandshear.  tr==NULL => inert targets (0p kernels).
+// tu,tv (and tq for vort/shear) are in/out, accumulated into like the reference does.
+int o2dref_points_on_points(int results_type,
+                            int ns, const float* sx, const float* sy, const float* ss, const float* sr,
+                            int nt, const float* tx, const float* ty, const float* tr,
+                            float* tu, float* tv, float* tq) {
+  if (results_type != velonly && results_type != velandvort && results_type != velandshear) return -1;
+  StdoutMute mute;
+  Points<float> src = make_points(ns, sx, sy, ss, sr);
+  Points<float> targ = tr ? make_points(nt, tx, ty, tx /*dummy strengths*/, tr)
+                          : make_points(nt, tx, ty, nullptr, nullptr);
+  auto& u = targ.get_vel();
+  for (int i = 0; i < nt; ++i) { u[0][i] = tu[i]; u[1][i] = tv[i]; }
+  if (results_type == velandvort) { auto& w = targ.get_vort();  for (int i = 0; i < nt; ++i) w[i] = tq[i]; }
+  if (results_type == velandshear) { auto& e = targ.get_shear(); for (int i = 0; i < nt; ++i) e[i] = tq[i]; }
+  ExecEnv env(true, direct, cpu_x86);
+  points_affect_points<float,double>(src, targ, ResultsType((results_t)results_type), env);
+  for (int i = 0; i < nt; ++i) { tu[i] = u[0][i]; tv[i] = u[1][i]; }
+  if (results_type == velandvort) { auto& w = targ.get_vort();  for (int i = 0; i < nt; ++i) tq[i] = w[i]; }
+  if (results_type == velandshear) { auto& e = targ.get_shear(); for (int i = 0; i < nt; ++i) tq[i] = e[i]; }
+  return 0;
+}
+
+// velocity + 2x2 gradient: restated loop (shape of src/Influence.h:347-361) around the
+// reference's own kernelug_0v_0b (src/Kernels.h:112-133).  skip_self!=0 drops i==j when
+// source and target arrays are the same set (needed for the EXP core).
+int o2dref_points_on_points_grad(int ns, const float* sx, const float* sy, const float* ss, const float* sr,
+                                 int nt, const float* tx, const float* ty, const float* tr,
+                                 float* tu, float* tv, float* tux, float* tvx, float* tuy, float* tvy,
+                                 int skip_self) {
+  #pragma omp parallel for
+  for (int32_t i = 0; i < (int32_t)nt; ++i) {
+    double au = 0.0, av = 0.0, aux = 0.0, avx = 0.0, auy = 0.0, avy = 0.0;
+    for (int j = 0; j < ns; ++j) {
+      if (skip_self && j == i) continue;
+      kernelug_0v_0b<float,double>(sx[j], sy[j], sr[j], ss[j], tx[i], ty[i], tr[i],
+                                   &au, &av, &aux, &avx, &auy, &avy);
+    }
+    tu[i] += au;  tv[i] += av;
+    tux[i] += aux; tvx[i] += avx; tuy[i] += auy; tvy[i] += avy;
+  }
+  return 0;
+}
+
+// reference panels_affect_points<float,double> (src/Influence.h:422-614); always the
+// vortex+source kernel kernelu_1vs_0p because Surfaces engages ps[1].
+int o2dref_panels_on_points(int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                            const float* vs, const float* ss,
+                            int nt, const float* tx, const float* ty, float* tu, float* tv) {
+  StdoutMute mute;
+  Surfaces<float> src = make_surfaces(np, nnodes, nx, ny, idx, vs, ss);
+  Points<float> targ = make_points(nt, tx, ty, nullptr, nullptr);
+  auto& u = targ.get_vel();
+  for (int i = 0; i < nt; ++i) { u[0][i] = tu[i]; u[1][i] = tv[i]; }
+  ExecEnv env(true, direct, cpu_x86);
+  panels_affect_points<float,double>(src, targ, ResultsType(velonly), env);
+  for (int i = 0; i < nt; ++i) { tu[i] = u[0][i]; tv[i] = u[1][i]; }
+  return 0;
+}
+
+// vortex-only panels: restated have_source_strengths==false branch (src/Influence.h:576-594)
+// around the reference's own kernelu_1v_0p (src/Kernels.h:312-354).
+int o2dref_panels_on_points_vortex(int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                                   const float* vs,
+                                   int nt, const float* tx, const float* ty, float* tu, float* tv) {
+  (void)nnodes;
+  #pragma omp parallel for
+  for (int32_t i = 0; i < (int32_t)nt; ++i) {
+    double au = 0.0, av = 0.0, ru = 0.0, rv = 0.0;
+    for (int j = 0; j < np; ++j) {
+      const size_t j0 = idx[2*j], j1 = idx[2*j+1];
+      kernelu_1v_0p<float,double>(nx[j0], ny[j0], nx[j1], ny[j1], vs[j], tx[i], ty[i], &ru, &rv);
+      au += ru; av += rv;
+    }
+    tu[i] += au; tv[i] += av;
+  }
+  return 0;
+}
+
+// reference points_affect_panels<float,double> (src/Influence.h:633-771): particle
+// velocities on panel centres by reciprocity, pu -= (1/area) * sum.  Panel areas are
+// the ones Surfaces::compute_bases derives (src/Surfaces.h:682-726) and are returned
+// through `area` (may be NULL) so a caller can feed the same values elsewhere.
+int o2dref_points_on_panels(int ns, const float* sx, const float* sy, const float* ss,
+                            int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                            float* pu, float* pv, float* area) {
+  StdoutMute mute;
+  std::vector<float> rad((size_t)ns, 1.0f);
+  Points<float> src = make_points(ns, sx, sy, ss, rad.data());
+  Surfaces<float> targ = make_surfaces(np, nnodes, nx, ny, idx, nullptr, nullptr);
+  auto& u = targ.get_vel();
+  for (int i = 0; i < np; ++i) { u[0][i] = pu[i]; u[1][i] = pv[i]; }
+  ExecEnv env(true, direct, cpu_x86);
+  points_affect_panels<float,double>(src, targ, ResultsType(velonly), env);
+  for (int i = 0; i < np; ++i) { pu[i] = u[0][i]; pv[i] = u[1][i]; }
+  if (area) { const auto& a = targ.get_area(); for (int i = 0; i < np; ++i) area[i] = a[i]; }
+  return 0;
+}
+
+// reference points_affect_points_vorticity<float,double> (src/InfluenceVort.h:47-126)
+int o2dref_points_vorticity(int ns, const float* sx, const float* sy, const float* ss, const float* sr,
+                            int nt, const float* tx, const float* ty, float* tw) {
+  StdoutMute mute;
+  Points<float> src = make_points(ns, sx, sy, ss, sr);
+  Points<float> targ = make_points(nt, tx, ty, nullptr, nullptr);
+  auto& w = targ.get_vort();
+  for (int i = 0; i < nt; ++i) w[i] = tw[i];
+  ExecEnv env(true, direct, cpu_x86);
+  points_affect_points_vorticity<float,double>(src, targ, env);
+  for (int i = 0; i < nt; ++i) tw[i] = w[i];
+  return 0;
+}
+
+// reference ElementBase::finalize_vels (src/ElementBase.h:215-234) through Points
+int o2dref_finalize_vels(int n, float* u, float* v, float* w, float* e, double fsx, double fsy) {
+  StdoutMute mute;
+  std::vector<float> zeros((size_t)n, 0.0f);
+  Points<float> p = make_points(n, zeros.data(), zeros.data(), nullptr, nullptr);
+  auto& vel = p.get_vel();
+  for (int i = 0; i < n; ++i) { vel[0][i] = u[i]; vel[1][i] = v[i]; }
+  if (w) { auto& pw = p.get_vort();  for (int i = 0; i < n; ++i) pw[i] = w[i]; }
+  if (e) { auto& pe = p.get_shear(); for (int i = 0; i < n; ++i) pe[i] = e[i]; }
+  p.finalize_vels(std::array<double,Dimensions>({fsx, fsy}));
+  for (int i = 0; i < n; ++i) { u[i] = vel[0][i]; v[i] = vel[1][i]; }
+  if (w) { auto& pw = p.get_vort();  for (int i = 0; i < n; ++i) w[i] = pw[i]; }
+  if (e) { auto& pe = p.get_shear(); for (int i = 0; i < n; ++i) e[i] = pe[i]; }
+  return 0;
+}
+
+}  // extern "C"

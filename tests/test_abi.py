@@ -1,0 +1,57 @@
+"""CPU: the C-ABI library loads and exports every symbol include/omega2d_b200.h declares; with no
+GPU it fails loudly (no CPU fallback); its flop accounting equals the reference's counters."""
+import ctypes
+import re
+
+import pytest
+
+import omega2d_b200 as o2d
+import oracle
+
+
+def declared_functions():
+    text = open(o2d.HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = re.findall(r"\b(o2d_[a-z0-9_]+|external_vel_solver_[a-z_]+)\s*\(", text)
+    return sorted(set(names))
+
+
+def test_header_symbols_exported():
+    lib = o2d.load_library()
+    names = declared_functions()
+    assert len(names) >= 24, names
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/omega2d_b200.h but not exported"
+
+
+def test_no_gpu_means_error_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(o2d.O2DError) as ei:
+        o2d.Context(0)
+    assert ei.value.code == o2d.ERR_NO_DEVICE
+    assert "no CPU fallback" in str(ei.value)
+    # the legacy plugin symbols report failure through a negative flop count
+    import numpy as np
+    a = np.zeros(4, np.float32)
+    with pytest.raises(o2d.O2DError):
+        o2d.external_vel_solver(a, a, a, a + 1, a, a)
+
+
+@pytest.mark.parametrize("core", oracle.CORES)
+def test_flops_match_reference_counters(core, port):
+    # oracle 'which': 0 u, 1 uw, 2 ue, 3 ug ; library results_t: 1, 4, 5, 2
+    for which, res in ((0, o2d.VELONLY), (1, o2d.VELANDVORT), (2, o2d.VELANDSHEAR)):
+        for blob in (False, True):
+            assert o2d.flops_per_pair(0, core, res, blob) == port.flops(core, which, blob)
+    assert o2d.flops_per_pair(0, core, o2d.VELANDGRAD, True) == port.flops(core, 3, True)
+    assert o2d.flops_per_pair(1) == port.flops(core, 4, False) == 39
+    assert o2d.flops_per_pair(2) == port.flops(core, 5, False) == 47
+    assert o2d.flops_per_pair(3) == port.flops(core, 6, False) == 13
+
+
+def test_default_core_is_the_references_default():
+    lib = o2d.load_library()
+    assert lib.o2d_get_default_core() == o2d.CORE_ID["v2"]   # reference src/CoreFunc.h:38
+    assert lib.o2d_set_default_core(99) == o2d.ERR_INVALID

@@ -1,0 +1,193 @@
+"""GPU: the CUDA path, called through the C ABI, against the oracle.
+
+Tolerance is BASELINE.json's: max_i ||du_i|| / max_i ||u_i|| <= 1e-5 (float32), applied to
+velocities, vorticity, shear and every gradient component.  Oracle = the C restatement
+(pinned to the reference by the CPU tests) and the committed reference golden vectors."""
+import numpy as np
+import pytest
+
+import omega2d_b200 as o2d
+import oracle
+from omega2d_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+RES = {"u": o2d.VELONLY, "uw": o2d.VELANDVORT, "ue": o2d.VELANDSHEAR}
+
+
+@pytest.mark.parametrize("core", o2d.CORES)
+@pytest.mark.parametrize("blob", [0, 1])
+def test_golden_vectors(core, blob, ctx, golden):
+    g = golden
+    tr = g["tr"] if blob else None
+    got = ctx.points_on_points_np(core, o2d.VELONLY, g["sx"], g["sy"], g["ss"], g["sr"], g["tx"], g["ty"], tr)
+    assert W.rel_err(got, tuple(g[f"{core}_u_{blob}"])) < TOL
+    sl = slice(40, None) if core == "exp" else slice(None)
+    trs = None if tr is None else tr[sl]
+    for key in ("uw", "ue"):
+        got = ctx.points_on_points_np(core, RES[key], g["sx"], g["sy"], g["ss"], g["sr"], g["tx"][sl], g["ty"][sl], trs)
+        want = g[f"{core}_{key}_{blob}"]
+        assert W.rel_err(got[:2], (want[0], want[1])) < TOL
+        assert W.rel_err(got[2], want[2]) < TOL, (core, key, blob)
+    if blob:
+        got = ctx.points_on_points_np(core, o2d.VELANDGRAD, g["sx"], g["sy"], g["ss"], g["sr"],
+                                      g["tx"][sl], g["ty"][sl], g["tr"][sl])
+        want = g[f"{core}_ug_1"]
+        assert W.rel_err(got[:2], (want[0], want[1])) < TOL
+        for k in range(2, 6):
+            assert W.rel_err(got[k], want[k]) < TOL, (core, "grad", k)
+        np.testing.assert_array_equal(got[2], -got[5])   # ux + vy == 0 exactly, as in the reference
+
+
+@pytest.mark.parametrize("core", o2d.CORES)
+@pytest.mark.parametrize("ns,nt", [(1, 1), (2, 3), (1023, 257), (1024, 1024), (1025, 1025), (5000, 2049), (20000, 777)])
+def test_ragged_sizes_vs_oracle(core, ns, nt, ctx, port):
+    sx, sy, ss, sr = W.onbody_random(ns, seed=ns)
+    tx, ty, _, tr = W.onbody_random(nt, seed=nt + 1)
+    want = port.points_on_points(core, oracle.VELONLY, sx, sy, ss, sr, tx, ty, tr)
+    got = ctx.points_on_points_np(core, o2d.VELONLY, sx, sy, ss, sr, tx, ty, tr)
+    assert W.rel_err(got, want) < TOL
+
+
+def test_empty_inputs_are_noops(ctx):
+    e = np.zeros(0, np.float32)
+    a = np.ones(5, np.float32)
+    u, v = ctx.points_on_points_np("v2", o2d.VELONLY, e, e, e, e, a, a, a, init=(a * 3, a * 4))
+    assert (u == 3).all() and (v == 4).all()
+    u, v = ctx.points_on_points_np("v2", o2d.VELONLY, a, a, a, a, e, e, e)
+    assert u.size == 0
+
+
+def test_accumulate_semantics(ctx, golden):
+    g = golden
+    got = ctx.points_on_points_np("v2", o2d.VELONLY, g["sx"], g["sy"], g["ss"], g["sr"], g["tx"], g["ty"], g["tr"],
+                                  init=(g["u0"], g["v0"]))
+    assert W.rel_err(got, tuple(g["v2_u_1_accum"])) < TOL
+
+
+def test_self_interaction_targets_are_sources(ctx, port):
+    """C1 shape: targets == sources (self pairs included, contribute 0 to u,v and core(0) to w)."""
+    x, y, s, r = W.c1_speedtest(4000)
+    for core in ("v2", "rm", "wl"):
+        want = port.points_on_points(core, oracle.VELANDVORT, x, y, s, r, x, y, r)
+        got = ctx.points_on_points_np(core, o2d.VELANDVORT, x, y, s, r, x, y, r)
+        assert W.rel_err(got[:2], want[:2]) < TOL
+        assert W.rel_err(got[2], want[2]) < TOL
+
+
+def test_exp_gradient_nan_matches_reference(ctx, golden):
+    g = golden
+    u, v, w = ctx.points_on_points_np("exp", o2d.VELANDVORT, g["sx"], g["sy"], g["ss"], g["sr"],
+                                      g["tx"][:40], g["ty"][:40], g["tr"][:40])
+    assert np.isfinite(u).all() and np.isfinite(v).all() and np.isnan(w).all()
+
+
+def test_unsupported_and_invalid(ctx):
+    a = np.ones(4, np.float32)
+    with pytest.raises(o2d.O2DError) as ei:
+        ctx.points_on_points("v2", o2d.PSIONLY, o2d.MEM_HOST, 4, a, a, a, a, 4, a, a, a, a.copy(), a.copy())
+    assert ei.value.code == o2d.ERR_UNSUPPORTED
+    with pytest.raises(o2d.O2DError) as ei:
+        ctx.points_on_points(7, o2d.VELONLY, o2d.MEM_HOST, 4, a, a, a, a, 4, a, a, a, a.copy(), a.copy())
+    assert ei.value.code == o2d.ERR_INVALID
+    with pytest.raises(o2d.O2DError) as ei:   # vorticity requested without an output array
+        ctx.points_on_points("v2", o2d.VELANDVORT, o2d.MEM_HOST, 4, a, a, a, a, 4, a, a, a, a.copy(), a.copy())
+    assert ei.value.code == o2d.ERR_INVALID
+
+
+def test_panels_golden(ctx, golden):
+    g = golden
+    got = ctx.panels_on_points_np(g["nx"], g["ny"], g["idx"], g["vs"], g["sps"], g["px"], g["py"])
+    assert W.rel_err(got, tuple(g["pan_vs"])) < TOL
+    got = ctx.panels_on_points_np(g["nx"], g["ny"], g["idx"], g["vs"], None, g["px"], g["py"])
+    assert W.rel_err(got, tuple(g["pan_v"])) < TOL
+    got = ctx.points_on_panels_np(g["px"], g["py"], g["ps"], g["nx"], g["ny"], g["idx"], g["area"])
+    assert W.rel_err(got, tuple(g["ptpan"])) < TOL
+
+
+@pytest.mark.parametrize("npan,nt", [(1, 5), (143, 10000), (257, 300), (5000, 4096)])
+def test_panels_vs_oracle(npan, nt, ctx, port):
+    nx, ny, idx, vs, ss = W.circle_panels(max(npan, 3), radius=0.5, seed=npan)
+    nx, ny = nx, ny
+    idx, vs, ss = idx[:2 * npan], vs[:npan], ss[:npan]
+    x, y, s, r = W.annulus_blobs(nt, seed=nt)
+    want = port.panels_on_points(nx, ny, idx, vs, ss, x, y)
+    got = ctx.panels_on_points_np(nx, ny, idx, vs, ss, x, y)
+    assert W.rel_err(got, want) < TOL
+    area = port.panel_areas(nx, ny, idx)
+    want = port.points_on_panels(x, y, s, nx, ny, idx, area)
+    got = ctx.points_on_panels_np(x, y, s, nx, ny, idx, area)
+    assert W.rel_err(got, want) < TOL
+
+
+def test_closed_ring_property(ctx):
+    nx, ny, idx, vs, _ = W.circle_panels(2000, radius=0.5)
+    vs[:] = 1.0
+    rng = np.random.default_rng(0)
+    rho = 0.4 * np.sqrt(rng.uniform(0, 1, 5000)); th = rng.uniform(0, 6.2832, 5000)
+    tx = (rho * np.cos(th)).astype(np.float32); ty = (rho * np.sin(th)).astype(np.float32)
+    u, v = ctx.panels_on_points_np(nx, ny, idx, vs, None, tx, ty)
+    assert np.abs(u).max() < 2e-5 and np.abs(v).max() < 2e-5
+
+
+def test_vorticity(ctx, golden, port):
+    g = golden
+    got = ctx.points_vorticity_np(g["sx"], g["sy"], g["ss"], g["sr"], g["tx"], g["ty"])
+    assert W.rel_err(got, g["vort"]) < TOL
+    sx, sy, ss, sr = W.gaussian_blob(6000, seed=3)
+    want = port.points_vorticity(sx, sy, ss, sr, sx[:1500], sy[:1500])
+    got = ctx.points_vorticity_np(sx, sy, ss, sr, sx[:1500], sy[:1500])
+    assert W.rel_err(got, want) < TOL
+
+
+def test_finalize_and_zero(ctx, golden):
+    g = golden
+    uw = g["v2_uw_1"]
+    u, v, w = uw[0].copy(), uw[1].copy(), uw[2].copy()
+    ctx.finalize_vels(o2d.MEM_HOST, u.size, u, v, w, None, (1.0, -0.5))
+    np.testing.assert_array_equal(np.stack([u, v, w]), g["fin"])
+    ctx.zero_vels(o2d.MEM_HOST, u.size, u, v, w, None)
+    assert not u.any() and not v.any() and not w.any()
+
+
+def test_legacy_plugin_symbols(ctx, port):
+    """external_vel_solver_f_/_tr_f_ as Omega2D calls them (reference src/Influence.h:82-88)."""
+    sx, sy, ss, sr = W.onbody_random(3000, seed=8)
+    tx, ty, _, tr = W.onbody_random(500, seed=9)
+    u0 = np.full(500, 0.25, np.float32)
+    tu, tv, flops = o2d.external_vel_solver(sx, sy, ss, sr, tx, ty, tr, tu=u0, tv=u0)
+    want = port.points_on_points("v2", oracle.VELONLY, sx, sy, ss, sr, tx, ty, tr, u0, u0)
+    assert W.rel_err((tu, tv), want) < TOL
+    assert flops == pytest.approx(500 * (2.0 + 19.0 * 3000), rel=1e-6)
+    tu, tv, flops = o2d.external_vel_solver(sx, sy, ss, sr, tx, ty, None)
+    want = port.points_on_points("v2", oracle.VELONLY, sx, sy, ss, sr, tx, ty, None)
+    assert W.rel_err((tu, tv), want) < TOL
+    assert flops == pytest.approx(500 * (2.0 + 16.0 * 3000), rel=1e-6)
+
+
+def test_device_memory_path_and_determinism(ctx):
+    import torch
+    sx, sy, ss, sr = W.gaussian_blob(50000, seed=5)
+    dev = torch.device("cuda:0")
+    t = [torch.from_numpy(a).to(dev) for a in (sx, sy, ss, sr)]
+    outs = []
+    for _ in range(2):
+        tu = torch.zeros(50000, device=dev); tv = torch.zeros(50000, device=dev)
+        ctx.points_on_points("rm", o2d.VELONLY, o2d.MEM_DEVICE, 50000, *t, 50000, t[0], t[1], t[3], tu, tv)
+        ctx.synchronize()
+        outs.append((tu.cpu().numpy(), tv.cpu().numpy()))
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])   # bit-reproducible
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])
+    host = ctx.points_on_points_np("rm", o2d.VELONLY, sx, sy, ss, sr, sx, sy, sr)
+    np.testing.assert_array_equal(host[0], outs[0][0])      # host path == device path
+
+
+def test_sharded_single_rank_equals_plain(ctx):
+    """o2d_points_on_points_sharded with one rank (no communicator) takes the chunked
+    local-block path and must equal the plain call bit for bit."""
+    sx, sy, ss, sr = W.gaussian_blob(30000, seed=6)
+    a = ctx.points_on_points_np("v2", o2d.VELONLY, sx, sy, ss, sr, sx, sy, sr)
+    tu = np.zeros(30000, np.float32); tv = np.zeros(30000, np.float32)
+    ctx.points_on_points_sharded("v2", o2d.VELONLY, o2d.MEM_HOST, 30000, 30000, sx, sy, ss, sr,
+                                 30000, sx, sy, sr, tu, tv)
+    assert W.rel_err((tu, tv), a) < 1e-7
