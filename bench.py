@@ -233,7 +233,10 @@ def run_ours(args, wl, n1):
         uid = [o2d.Context.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(world, rank, uid[0])
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream shared by torch and the library: torch's default stream has
+    # handle 0, which o2d_set_stream reads as "use the context's own stream"
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     info = ctx.device_info()
 
@@ -332,7 +335,9 @@ def run_ours(args, wl, n1):
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e_steps,
                "api": "o2d_points_on_points[_sharded](O2D_MEM_HOST) on pinned host arrays"}
         # host path and device path must agree bit for bit
-        assert np.array_equal(houts[0][:nloc].numpy(), u), "host-memory path disagrees with device path"
+        if not np.array_equal(houts[0][:nloc].numpy(), u):
+            bad = int((houts[0][:nloc].numpy() != u).sum())
+            raise SystemExit(f"bench.py: host-memory path disagrees with device path on {bad} of {nloc} targets")
 
     if rank != 0:
         if world > 1:

@@ -75,6 +75,62 @@ __host__ __device__ __forceinline__ float radius_term(float r) {
   return r2;
 }
 
+// ---- compact-exponential core, one lane -------------------------------------------------------
+// reference src/CoreFunc.h:118-130 (exp_cond), :144-150, :170-179:
+//   ood2 = 1/d2, corefac = 1/(sr^2+tr^2), x = reld2 = corefac/ood2
+//   K   = ood2 (x>16) | corefac (x<0.001) | ood2 (1-exp(-x))
+//   bbb = -2 K ood2 + 2 corefac ood2 exp(-x)                     (NaN at d2 == 0, as the reference)
+// The reference forms 1-exp(-x) and the bbb difference in float with heavy cancellation for
+// x << 1 (its own result carries ~6e-8/x relative noise there).  Here both are evaluated in
+// cancellation-free form so the only disagreement left is the reference's own rounding:
+//   1-exp(-x) = x P(x)                         (Taylor, x < 0.5)
+//   bbb = 2 corefac ood2 g(x),  g(x) = exp(-x) - (1-exp(-x))/x = sum_n (-1)^n n x^n/(n+1)!   (0.001<=x<0.5)
+// while keeping the reference's three branches (including its x<0.001 branch, where K is
+// replaced by corefac inside the bbb expression too).
+template <bool GRAD>
+__device__ __forceinline__ void exp_core_lane(float d2, float sig2, float& K, float& B) {
+  const float ood2 = mufu_rcp(d2);
+  const float corefac = mufu_rcp(sig2);
+  const float x = d2 * corefac;
+  const float e = mufu_ex2(-1.4426950408889634f * x);
+  float em1;   // 1 - exp(-x)
+  if (x < 0.5f) {
+    float p = -1.0f / 40320.0f;
+    p = fmaf(p, x, 1.0f / 5040.0f);
+    p = fmaf(p, x, -1.0f / 720.0f);
+    p = fmaf(p, x, 1.0f / 120.0f);
+    p = fmaf(p, x, -1.0f / 24.0f);
+    p = fmaf(p, x, 1.0f / 6.0f);
+    p = fmaf(p, x, -0.5f);
+    p = fmaf(p, x, 1.0f);
+    em1 = x * p;
+  } else {
+    em1 = 1.0f - e;
+  }
+  K = x > 16.0f ? ood2 : (x < 0.001f ? corefac : ood2 * em1);
+  if (GRAD) {
+    float g;   // bbb = 2 ood2 * g
+    if (x > 16.0f) {
+      g = fmaf(corefac, e, -ood2);
+    } else if (x < 0.001f) {
+      g = -corefac * em1;
+    } else if (x < 0.5f) {
+      float q = 1.0f / 45360.0f;
+      q = fmaf(q, x, -1.0f / 5760.0f);
+      q = fmaf(q, x, 1.0f / 840.0f);
+      q = fmaf(q, x, -1.0f / 144.0f);
+      q = fmaf(q, x, 1.0f / 30.0f);
+      q = fmaf(q, x, -0.125f);
+      q = fmaf(q, x, 1.0f / 3.0f);
+      q = fmaf(q, x, -0.5f);
+      g = corefac * (x * q);
+    } else {
+      g = fmaf(corefac, e, -K);
+    }
+    B = 2.0f * ood2 * g;
+  }
+}
+
 // ---- core functions on packed lanes ----------------------------------------------------------
 // Inputs per lane: dx,dy = target - source, rho = source radius term, tau = target radius term.
 // Outputs: K (the reference's core_func return / *r2), d2 = dx^2+dy^2 (only valid when GRAD or
@@ -123,22 +179,10 @@ __device__ __forceinline__ void core_eval(float2 dx, float2 dy, float2 rho, floa
     K = fma2(mul2(s2, r), r, r);
     if (GRAD) B = mul2(fma2(mul2(f2(-4.0f), K), D, f2(2.0f)), mul2(r, r));
   } else {  // CORE_EXP
-    // src/CoreFunc.h:118-130,144-150,170-179: ood2 = 1/d2, corefac = 1/(sr^2+tr^2),
-    // reld2 = corefac/ood2; K = ood2 (reld2>16) | corefac (reld2<0.001) | ood2 (1-exp(-reld2));
-    // bbb = -2 K ood2 + 2 corefac ood2 exp(-reld2)   (NaN at d2 == 0, as in the reference)
     d2 = fma2(dy, dy, mul2(dx, dx));
-    const float2 ood2 = rcp2(d2);
-    const float2 corefac = rcp2(add2(rho, tau));
-    const float2 reld2 = mul2(d2, corefac);
-    const float kLog2e = 1.4426950408889634f;
-    const float2 ex = make_float2(mufu_ex2(-kLog2e * reld2.x), mufu_ex2(-kLog2e * reld2.y));
-    const float2 mid = mul2(ood2, fma2(ex, f2(-1.0f), f2(1.0f)));
-    K.x = reld2.x > 16.0f ? ood2.x : (reld2.x < 0.001f ? corefac.x : mid.x);
-    K.y = reld2.y > 16.0f ? ood2.y : (reld2.y < 0.001f ? corefac.y : mid.y);
-    if (GRAD) {
-      const float2 t = mul2(mul2(f2(2.0f), corefac), mul2(ood2, ex));
-      B = fma2(mul2(f2(-2.0f), K), ood2, t);
-    }
+    const float2 sig2 = add2(rho, tau);
+    exp_core_lane<GRAD>(d2.x, sig2.x, K.x, B.x);
+    exp_core_lane<GRAD>(d2.y, sig2.y, K.y, B.y);
   }
 }
 

@@ -105,10 +105,23 @@ def test_panels_golden(ctx, golden):
     assert W.rel_err(got, tuple(g["ptpan"])) < TOL
 
 
+def _panel_check(got, want, exact):
+    """Within 1e-5 of the oracle -- unless the oracle's float32 formulation (difference of two
+    atan2f, log of a ratio, reference src/Kernels.h:262-268,338) is itself further than that from
+    exact (float64) arithmetic, which happens for short panels; then: within 1e-5 of exact and no
+    further from the oracle than 1.5x the oracle's own error."""
+    noise = W.rel_err(want, exact)
+    assert W.rel_err(got, exact) < TOL, ("vs exact", W.rel_err(got, exact))
+    assert W.rel_err(got, want) < max(TOL, 1.5 * noise), ("vs oracle", W.rel_err(got, want), "oracle noise", noise)
+
+
 @pytest.mark.parametrize("npan,nt", [(1, 5), (143, 10000), (257, 300), (5000, 4096)])
 def test_panels_vs_oracle(npan, nt, ctx, port):
+    """Smooth sheet strengths (flow-over-cylinder like: vs ~ sin(theta)), the physically relevant case."""
+    from f64ref import panels_on_points_f64, points_on_panels_f64
     nx, ny, idx, vs, ss = W.circle_panels(max(npan, 3), radius=0.5, seed=npan)
-    nx, ny = nx, ny
+    th = np.arctan2(ny, nx)
+    vs = (2.0 * np.sin(th) + 0.3).astype(np.float32); ss = (0.5 * np.cos(th)).astype(np.float32)
     idx, vs, ss = idx[:2 * npan], vs[:npan], ss[:npan]
     x, y, s, r = W.annulus_blobs(nt, seed=nt)
     want = port.panels_on_points(nx, ny, idx, vs, ss, x, y)
@@ -117,7 +130,18 @@ def test_panels_vs_oracle(npan, nt, ctx, port):
     area = port.panel_areas(nx, ny, idx)
     want = port.points_on_panels(x, y, s, nx, ny, idx, area)
     got = ctx.points_on_panels_np(x, y, s, nx, ny, idx, area)
-    assert W.rel_err(got, want) < TOL
+    _panel_check(got, want, points_on_panels_f64(x, y, s, nx, ny, idx, area))
+
+
+def test_panels_random_strengths_noise_floor(ctx, port):
+    """5000 short panels with RANDOM +-1 strengths: the far field nearly cancels and the float32
+    reference formulation carries rounding noise above 1e-5 of max|u| by itself (3.8e-5 here)."""
+    from f64ref import panels_on_points_f64
+    nx, ny, idx, vs, ss = W.circle_panels(5000, radius=0.5, seed=5000)
+    x, y, _, _ = W.annulus_blobs(2048, seed=4096)
+    want = port.panels_on_points(nx, ny, idx, vs, ss, x, y)
+    got = ctx.panels_on_points_np(nx, ny, idx, vs, ss, x, y)
+    _panel_check(got, want, panels_on_points_f64(nx, ny, idx, vs, ss, x, y))
 
 
 def test_closed_ring_property(ctx):
