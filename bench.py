@@ -94,7 +94,9 @@ def cpu_checker(core: str):
 def cpu_sample(wl, parts, seconds: float):
     """Time the CPU path on a strided target subset against ALL sources (onbody's ntskip
     method, reference extern/onbody/src/main2dvort.cpp:116-133), sized for ~`seconds`."""
+    import oracle
     kind, fn = cpu_checker(wl["core"])
+    oracle.set_threads()          # torchrun exports OMP_NUM_THREADS=1; use every host core
     sx, sy, ss, sr = parts
     n = sx.size
     res = 1 if wl["results"] == 2 else wl["results"]   # the reference has no velandgrad loop (SURVEY F5)
@@ -106,7 +108,9 @@ def cpu_sample(wl, parts, seconds: float):
         return time.perf_counter() - t0, sub, out
 
     cal = min(n, max(64, int(2e8 // max(n, 1))))
-    dt, _, _ = run(cal)                       # warm-up + calibration
+    run(cal)                                  # warm-up (thread team start-up, page faults)
+    cal = min(n, 8 * cal)
+    dt, _, _ = run(cal)                       # calibration
     rate = cal * n / max(dt, 1e-6)
     count = int(min(n, max(cal, seconds * rate / n)))
     return kind, run, count
@@ -127,7 +131,8 @@ def run_reference_arm(args, wl, n):
         times.append(dt)
     total = sum(times)
     value = args.steps * count * n / total
-    cores = os.cpu_count()
+    import oracle
+    cores = oracle.host_cores()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
@@ -372,7 +377,8 @@ def run_ours(args, wl, n1):
         dt, sub, ref_out = run(count)
         scale = np.sqrt(u.astype(np.float64) ** 2 + v.astype(np.float64) ** 2).max()
         err = np.sqrt((u[sub] - ref_out[0]).astype(np.float64) ** 2 + (v[sub] - ref_out[1]).astype(np.float64) ** 2).max() / scale
-        cpu = {"value": count * n / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
+        import oracle
+        cpu = {"value": count * n / dt, "unit": UNIT, "cores": oracle.host_cores(), "kind": kind,
                "sample": f"{count} strided targets x all {n} sources, one call, OpenMP on all host cores, USE_VC off",
                "seconds": dt, "max_rel_err_gpu_vs_cpu": float(err), "tolerance": 1e-5}
 

@@ -67,11 +67,10 @@ __device__ __forceinline__ void apply_outputs(const OutPtrs& o, int i, const dou
   }
 }
 
-template <int CORE, int RES, int THREADS, int TILE>
+template <int CORE, int RES, int THREADS, int TILE, int R = ResTraits<RES>::R, int UNROLL = 4>
 __global__ void __launch_bounds__(THREADS)
 pp_kernel(const PPArgs a) {
   using T = ResTraits<RES>;
-  constexpr int R = T::R;
   constexpr int NC = T::NCOMP;
   constexpr uint32_t TILE_BYTES = TILE * 16;
 
@@ -139,7 +138,7 @@ pp_kernel(const PPArgs a) {
 #pragma unroll
       for (int c = 0; c < NC; ++c) part[k][c] = f2(0.0f);
 
-#pragma unroll 4
+#pragma unroll UNROLL
     for (int p = 0; p < TILE / 2; ++p) {
       const float4 A = s[2 * p];      // x0 x1 y0 y1   (stored NEGATED: dx = tx + (-sx))
       const float4 B = s[2 * p + 1];  // s0 s1 rho0 rho1

@@ -1,0 +1,94 @@
+// Surfaces.h -- 1-D elements (straight two-node panels) with the accessor surface of the
+// reference container (src/Surfaces.h:59-270, :682-726, :755-774), restricted to what the
+// influence path reads and writes: node positions, panel node indices, panel lengths
+// ("area"), vortex and source sheet strengths, panel-centre velocities.
+#pragma once
+#ifndef OMEGA2D_REFERENCE_HEADERS
+#include "Points.h"
+
+template <class S>
+class Surfaces : public ElementBase<S> {
+public:
+  // value per panel: 1 (vortex strength) or 2 (vortex, source) entries in _elems.val
+  Surfaces(const ElementPacket<float>& _elems, const elem_t _e, const move_t _m)
+    : ElementBase<S>(_elems.x.size() / Dimensions, _e, _m), np(_elems.nelem) {
+    assert(_elems.ndim == 1 && "Input elements are not (1D) surfaces");
+    for (size_t d = 0; d < Dimensions; ++d) {
+      this->x[d].resize(this->n);
+      for (size_t i = 0; i < this->n; ++i) this->x[d][i] = _elems.x[Dimensions*i+d];
+      this->u[d].assign(this->n, S(0));
+      pu[d].assign(np, S(0));
+    }
+    idx.assign(_elems.idx.begin(), _elems.idx.end());
+    assert(idx.size() == 2 * np && "this layer handles two-node panels");
+    for (auto i : idx) { assert(i < this->n && "Some indicies are bad"); (void)i; }
+    compute_bases();
+    if (_e != inert) {
+      // like the reference, both sheet strengths always exist for non-inert surfaces
+      // (src/Surfaces.h:87-92), so panels_affect_points takes the vortex+source kernel
+      ps[0] = Vector<S>(np, S(0));
+      ps[1] = Vector<S>(np, S(0));
+      const size_t nvalper = np ? _elems.val.size() / np : 0;
+      for (size_t i = 0; i < np; ++i) {
+        if (nvalper >= 1) (*ps[0])[i] = _elems.val[nvalper*i];
+        if (nvalper >= 2) (*ps[1])[i] = _elems.val[nvalper*i+1];
+      }
+    }
+  }
+
+  size_t get_npanels() const { return np; }
+  const std::vector<Int>& get_idx() const { return idx; }
+  const Vector<S>& get_area() const { return area; }
+  // panel-centre velocities shadow the node velocities (reference src/Surfaces.h:241-243)
+  const std::array<Vector<S>,Dimensions>& get_vel() const { return pu; }
+  std::array<Vector<S>,Dimensions>&       get_vel()       { return pu; }
+  const Vector<S>& get_str() const { return *ps[0]; }
+  Vector<S>&       get_str()       { return *ps[0]; }
+  bool have_src_str() const { return (bool)ps[1]; }
+  const Vector<S>& get_src_str() const { return *ps[1]; }
+  Vector<S>&       get_src_str()       { return *ps[1]; }
+
+  // panel length and unit tangent (reference src/Surfaces.h:699-711)
+  void compute_bases() {
+    area.resize(np);
+    for (size_t i = 0; i < np; ++i) {
+      const size_t id0 = idx[2*i], id1 = idx[2*i+1];
+      const S dx = this->x[0][id1] - this->x[0][id0];
+      const S dy = this->x[1][id1] - this->x[1][id0];
+      area[i] = std::sqrt(dx*dx + dy*dy);
+    }
+  }
+
+  // collocation points offset along the panel normal (into the fluid: left of node0->node1),
+  // used by panels_affect_panels (reference src/Influence.h:783-784)
+  ElementPacket<float> represent_as_particles(const S _offset, const S /*_vdelta*/) const {
+    std::vector<float> px(2 * np);
+    for (size_t i = 0; i < np; ++i) {
+      const size_t id0 = idx[2*i], id1 = idx[2*i+1];
+      const S tx = (this->x[0][id1] - this->x[0][id0]) / area[i];
+      const S ty = (this->x[1][id1] - this->x[1][id0]) / area[i];
+      px[2*i]   = S(0.5) * (this->x[0][id0] + this->x[0][id1]) - _offset * ty;
+      px[2*i+1] = S(0.5) * (this->x[1][id0] + this->x[1][id1]) + _offset * tx;
+    }
+    return ElementPacket<float>(px, std::vector<Int>(), std::vector<float>(np, 0.0f), np, 0);
+  }
+
+  void zero_vels() {
+    for (size_t d = 0; d < Dimensions; ++d) std::fill(pu[d].begin(), pu[d].end(), S(0));
+    ElementBase<S>::zero_vels();
+  }
+  void finalize_vels(const std::array<double,Dimensions>& _fs) {
+    const double factor = 0.5 / M_PI;
+    for (size_t d = 0; d < Dimensions; ++d)
+      for (size_t i = 0; i < np; ++i) pu[d][i] = _fs[d] + pu[d][i] * factor;
+    ElementBase<S>::finalize_vels(_fs);
+  }
+
+protected:
+  size_t np;
+  std::vector<Int> idx;
+  Vector<S> area;
+  std::array<Vector<S>,Dimensions> pu;
+  std::array<std::optional<Vector<S>>,2> ps;
+};
+#endif

@@ -1,0 +1,32 @@
+#!/usr/bin/env bash
+# Compile checks of the C++ host mirror (no GPU needed):
+#  1. tests/cpp/test_find_vels.cpp against the mirror containers, linked with libomega2d_b200.so
+#     -> build/test_find_vels (run by tests/test_host_mirror.py on the GPU box);
+#  2. where /root/reference exists: InfluenceB200.h against the REFERENCE's own containers
+#     (-fsyntax-only), proving the header is a drop-in for src/Influence.h + src/InfluenceVort.h.
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+ROOT="$(cd "$HERE/../.." && pwd)"
+REF="${O2D_REFERENCE:-/root/reference}"
+mkdir -p "$ROOT/build"
+g++ -std=c++17 -O2 -Wall -I"$HERE" "$ROOT/tests/cpp/test_find_vels.cpp" \
+    -L"$ROOT/omega2d_b200" -lomega2d_b200 -Wl,-rpath,'$ORIGIN/../omega2d_b200' -o "$ROOT/build/test_find_vels"
+echo "built build/test_find_vels"
+if [ -d "$REF/src" ]; then
+  cat > "$ROOT/build/ref_containers_check.cpp" <<'CPP'
+// the reference's containers + this repository's influence header instead of Influence.h
+#include "Collection.h"
+#include "ResultsType.h"
+#include "ExecEnv.h"
+#define OMEGA2D_REFERENCE_HEADERS
+#include "InfluenceB200.h"
+#include "ConvectionB200.h"
+void instantiate(std::vector<Collection>& a, std::vector<Collection>& b, std::vector<Collection>& c) {
+  find_vels<float,double>({0.0, 0.0}, a, b, c, velandvort, true);
+  find_vort<float,double>(a, b, c);
+}
+CPP
+  g++ -std=c++17 -fsyntax-only -w -I"$REF/src" -I"$REF/lib" -I"$REF/lib/tinyexpr" -I"$REF/lib/tinyxml2" -I"$HERE" \
+      "$ROOT/build/ref_containers_check.cpp"
+  echo "InfluenceB200.h compiles against the reference's own Points/Surfaces/Volumes/Collection"
+fi

@@ -251,6 +251,25 @@ class Ref:
         return u, v, w, e
 
 
+def host_cores() -> int:
+    """Cores this process may run on (what OpenMP would use by default)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def set_threads(n: int | None = None) -> int:
+    """Set the OpenMP team size of the checkers.  torch.distributed.run exports
+    OMP_NUM_THREADS=1 into every rank; the CPU baseline must still use all host cores."""
+    n = n or host_cores()
+    try:
+        C.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+    except OSError:
+        pass
+    return n
+
+
 _port = None
 _refs = {}
 
