@@ -67,6 +67,57 @@ __device__ __forceinline__ void apply_outputs(const OutPtrs& o, int i, const dou
   }
 }
 
+// Sum one staged tile of TILE sources onto the thread's R targets (float partial sums, two lanes).
+// UNI = all R targets share one radius term (see core_eval): rho+tau is formed once per source pair.
+template <int CORE, int RES, int TILE, int R, int UNROLL, bool UNI>
+__device__ __forceinline__ void tile_sum(const float4* __restrict__ s, const float2 (&tx)[R], const float2 (&ty)[R],
+                                         const float2 (&tau)[R], float2 (&part)[R][ResTraits<RES>::NCOMP]) {
+  using T = ResTraits<RES>;
+#pragma unroll UNROLL
+  for (int p = 0; p < TILE / 2; ++p) {
+    const float4 A = s[2 * p];      // x0 x1 y0 y1   (stored NEGATED: dx = tx + (-sx))
+    const float4 B = s[2 * p + 1];  // s0 s1 rho0 rho1
+    const float2 nsx = f2(A.x, A.y), nsy = f2(A.z, A.w);
+    const float2 str = f2(B.x, B.y);
+    const float2 rho = (UNI && RES != RES_VORT) ? add2(f2(B.z, B.w), tau[0]) : f2(B.z, B.w);
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const float2 dx = add2(tx[k], nsx);
+      const float2 dy = add2(ty[k], nsy);
+      if (RES == RES_VORT) {
+        // src/InfluenceVort.h:109-114; str = 2 ss/sr^2, rho = log2(e)/sr^2
+        const float2 d2 = fma2(dy, dy, mul2(dx, dx));
+        const float2 arg = mul2(d2, rho);
+        const float2 e = make_float2(mufu_ex2(-arg.x), mufu_ex2(-arg.y));
+        part[k][0] = fma2(str, e, part[k][0]);
+      } else {
+        float2 K, Bb, d2;
+        core_eval<CORE, T::GRAD, UNI>(dx, dy, rho, tau[k], K, Bb, d2);
+        const float2 r2 = mul2(str, K);
+        part[k][0] = fma2(r2, dy, part[k][0]);
+        part[k][1] = fma2(r2, dx, part[k][1]);
+        if (RES == RES_UW) {
+          const float2 bb = mul2(str, Bb);
+          part[k][2] = fma2(bb, d2, part[k][2]);
+          part[k][3] = add2(part[k][3], r2);
+        } else if (RES == RES_UE) {
+          const float2 bb = mul2(str, Bb);
+          const float2 ab = make_float2(fabsf(bb.x), fabsf(bb.y));
+          part[k][2] = fma2(ab, d2, part[k][2]);
+        } else if (RES == RES_UG) {
+          const float2 bb = mul2(str, Bb);
+          const float2 bx = mul2(bb, dx);
+          const float2 by = mul2(bb, dy);
+          part[k][2] = fma2(bx, dy, part[k][2]);
+          part[k][3] = fma2(bx, dx, part[k][3]);
+          part[k][4] = fma2(by, dy, part[k][4]);
+          part[k][5] = add2(part[k][5], r2);
+        }
+      }
+    }
+  }
+}
+
 template <int CORE, int RES, int THREADS, int TILE, int R = ResTraits<RES>::R, int UNROLL = 4>
 __global__ void __launch_bounds__(THREADS)
 pp_kernel(const PPArgs a) {
@@ -113,6 +164,14 @@ pp_kernel(const PPArgs a) {
     if (RES != RES_VORT && a.tr != nullptr && ok) t = radius_term<CORE>(a.tr[i]);
     tau[k] = f2(t);
   }
+  // every thread's R targets share one radius term (inert targets; uniform-radius particle sets,
+  // the reference's normal case): take the cheaper tile_sum<UNI>.  The flag is made CTA-uniform so
+  // the tile loop's barriers stay convergent.  Out-of-range targets carry 0: they only send the
+  // last CTA of a blob-target launch down the general path.
+  bool uni_t = true;
+#pragma unroll
+  for (int k = 1; k < R; ++k) uni_t = uni_t && (tau[k].x == tau[0].x);
+  const bool uni = __syncthreads_and(uni_t) != 0;
 
   double acc[R][NC];
 #pragma unroll
@@ -138,48 +197,8 @@ pp_kernel(const PPArgs a) {
 #pragma unroll
       for (int c = 0; c < NC; ++c) part[k][c] = f2(0.0f);
 
-#pragma unroll UNROLL
-    for (int p = 0; p < TILE / 2; ++p) {
-      const float4 A = s[2 * p];      // x0 x1 y0 y1   (stored NEGATED: dx = tx + (-sx))
-      const float4 B = s[2 * p + 1];  // s0 s1 rho0 rho1
-      const float2 nsx = f2(A.x, A.y), nsy = f2(A.z, A.w);
-      const float2 str = f2(B.x, B.y), rho = f2(B.z, B.w);
-#pragma unroll
-      for (int k = 0; k < R; ++k) {
-        const float2 dx = add2(tx[k], nsx);
-        const float2 dy = add2(ty[k], nsy);
-        if (RES == RES_VORT) {
-          // src/InfluenceVort.h:109-114; str = 2 ss/sr^2, rho = log2(e)/sr^2
-          const float2 d2 = fma2(dy, dy, mul2(dx, dx));
-          const float2 arg = mul2(d2, rho);
-          const float2 e = make_float2(mufu_ex2(-arg.x), mufu_ex2(-arg.y));
-          part[k][0] = fma2(str, e, part[k][0]);
-        } else {
-          float2 K, Bb, d2;
-          core_eval<CORE, T::GRAD>(dx, dy, rho, tau[k], K, Bb, d2);
-          const float2 r2 = mul2(str, K);
-          part[k][0] = fma2(r2, dy, part[k][0]);
-          part[k][1] = fma2(r2, dx, part[k][1]);
-          if (RES == RES_UW) {
-            const float2 bb = mul2(str, Bb);
-            part[k][2] = fma2(bb, d2, part[k][2]);
-            part[k][3] = add2(part[k][3], r2);
-          } else if (RES == RES_UE) {
-            const float2 bb = mul2(str, Bb);
-            const float2 ab = make_float2(fabsf(bb.x), fabsf(bb.y));
-            part[k][2] = fma2(ab, d2, part[k][2]);
-          } else if (RES == RES_UG) {
-            const float2 bb = mul2(str, Bb);
-            const float2 bx = mul2(bb, dx);
-            const float2 by = mul2(bb, dy);
-            part[k][2] = fma2(bx, dy, part[k][2]);
-            part[k][3] = fma2(bx, dx, part[k][3]);
-            part[k][4] = fma2(by, dy, part[k][4]);
-            part[k][5] = add2(part[k][5], r2);
-          }
-        }
-      }
-    }
+    if (uni) tile_sum<CORE, RES, TILE, R, UNROLL, true>(s, tx, ty, tau, part);
+    else     tile_sum<CORE, RES, TILE, R, UNROLL, false>(s, tx, ty, tau, part);
     // fold this tile's float partial sums into the float64 accumulators
 #pragma unroll
     for (int k = 0; k < R; ++k)

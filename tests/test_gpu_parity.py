@@ -49,6 +49,31 @@ def test_ragged_sizes_vs_oracle(core, ns, nt, ctx, port):
     assert W.rel_err(got, want) < TOL
 
 
+@pytest.mark.parametrize("core", o2d.CORES)
+@pytest.mark.parametrize("res", ["u", "uw", "ue", "ug"])
+def test_uniform_and_mixed_target_radii(core, res, ctx, port):
+    """The kernel switches, CTA by CTA, to a cheaper loop when all of a thread's targets share one
+    radius (uniform-radius sets are the reference's normal case; inert targets likewise).  Cover
+    (i) all-uniform targets incl. a ragged last CTA and (ii) a target set whose first part is
+    uniform and whose tail is not, so both loops run inside one launch."""
+    restype = {"u": oracle.VELONLY, "uw": oracle.VELANDVORT, "ue": oracle.VELANDSHEAR, "ug": oracle.VELANDGRAD}[res]
+    mine = {"u": o2d.VELONLY, "uw": o2d.VELANDVORT, "ue": o2d.VELANDSHEAR, "ug": o2d.VELANDGRAD}[res]
+    sx, sy, ss, sr = W.onbody_random(6000, seed=21)
+    tx, ty, _, tr = W.onbody_random(3333, seed=22)
+    tx = tx + np.float32(3e-4)   # no coincident pairs (EXP gradient terms are NaN there, tested elsewhere)
+    for mode in ("uniform", "mixed"):
+        trr = tr.copy()
+        trr[: (3333 if mode == "uniform" else 2048)] = np.float32(0.0125)
+        if res == "ug":
+            want = port.points_on_points_grad(core, sx, sy, ss, sr, tx, ty, trr)
+        else:
+            want = port.points_on_points(core, restype, sx, sy, ss, sr, tx, ty, trr)
+        got = ctx.points_on_points_np(core, mine, sx, sy, ss, sr, tx, ty, trr)
+        assert W.rel_err(got[:2], want[:2]) < TOL, (mode, "vel")
+        for k in range(2, len(got)):
+            assert W.rel_err(got[k], want[k]) < TOL, (mode, k)
+
+
 def test_empty_inputs_are_noops(ctx):
     e = np.zeros(0, np.float32)
     a = np.ones(5, np.float32)

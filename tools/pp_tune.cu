@@ -68,16 +68,17 @@ double run_variant(const char* name, const PPArgs& base, int n, int sms, double*
 int main(int argc, char** argv) {
   int n = argc > 1 ? atoi(argv[1]) : 262144;
   int reps = argc > 2 ? atoi(argv[2]) : 3;
+  const bool uniform = argc > 3 && atoi(argv[3]) != 0;   // same radius for every particle
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   int sms = prop.multiProcessorCount;
-  printf("device %s, %d SMs, n=%d\n", prop.name, sms, n);
+  printf("device %s, %d SMs, n=%d, %s radii\n", prop.name, sms, n, uniform ? "uniform" : "per-particle");
   std::vector<float> x(n), y(n), s(n), r(n);
   srand(1);
   for (int i = 0; i < n; ++i) {
     float u1 = (rand() + 1.0f) / (RAND_MAX + 2.0f), u2 = rand() / (float)RAND_MAX;
     float g = sqrtf(-2 * logf(u1));
     x[i] = 0.25f * g * cosf(6.2831853f * u2); y[i] = 0.25f * g * sinf(6.2831853f * u2);
-    s[i] = 1.0f / n; r[i] = 1.5f / sqrtf((float)n) * (0.8f + 0.4f * (rand() / (float)RAND_MAX));
+    s[i] = 1.0f / n; r[i] = 1.5f / sqrtf((float)n) * (uniform ? 1.0f : 0.8f + 0.4f * (rand() / (float)RAND_MAX));
   }
   float *dx, *dy, *ds, *dr, *du, *dv; float4* packed; double* partial;
   int ntiles = (n + kTile - 1) / kTile;
