@@ -58,10 +58,22 @@ WORKLOADS = {
 }
 
 
-def make_particles(name: str, n: int):
+def make_particles(name: str, n: int, vary_radius: bool = True):
     if name == "c1":
         return W.c1_speedtest(n)
-    return W.gaussian_blob(n, seed=2024, vary_radius=True)
+    return W.gaussian_blob(n, seed=2024, vary_radius=vary_radius)
+
+
+def ncu_traffic(core: str, results: int, n: int):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum); None when no capture
+    of this exact (core, results, particle count) is on file."""
+    try:
+        tab = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return None
+    e = tab.get(f"{core}/res{results}/n{n}")
+    return None if e is None else e
 
 
 def parse_args():
@@ -76,6 +88,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of one cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-variants", action="store_true")
     return ap.parse_args()
 
 
@@ -358,9 +371,12 @@ def run_ours(args, wl, n1):
     peak_nominal = info["fp32_peak_tflops"]
     ffma = ctx.measure_fp32_peak(False)
     ffma2 = ctx.measure_fp32_peak(True)
+    traffic = ncu_traffic(core, results, n) if world == 1 else None
     roofline = {
         "bound": "fp32", "achieved": achieved, "peak": peak_nominal, "unit": "TFLOP/s",
-        "frac": achieved / peak_nominal if peak_nominal else None, "traffic": None,
+        "frac": achieved / peak_nominal if peak_nominal else None,
+        "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
+        "algorithmic_bytes_per_launch": 16 * n + 12 * nloc + 4 * nout * nloc,
         "flops_per_pair": flops_pp, "kernel": f"pp_kernel<{core},res{results}>",
         "kernel_ms_per_step": kern_s * 1e3,
         "peak_source": f"nominal: {info['sm_count']} SMs x 128 lanes x 2 x {info['sm_clock_mhz']} MHz "
@@ -369,6 +385,73 @@ def run_ours(args, wl, n1):
         "frac_of_measured_ffma2": achieved / ffma2 if ffma2 else None,
         "note": "flops are the reference's own per-pair counters (src/Kernels.h, src/CoreFunc.h), not hardware ops",
     }
+
+    # ---- other kernels of the path on the same particle count (device-resident, kernel-only view) -----------
+    variants = None
+    if world == 1 and not args.no_variants and args.workload == "c3":
+        variants = []
+        for vname, vcore, vres, vary in (("uniform radius 1.5/sqrt(N) (SURVEY 8d C3 as written; the reference's normal case)", "rm", 1, False),
+                                         ("velocity + gradient (kernelug_0v_0b), per-particle radii", "rm", 2, True),
+                                         ("Vatistas-2 core (reference default), uniform radius", "v2", 1, False)):
+            vp = make_particles(args.workload, n, vary_radius=vary)
+            vd = [torch.from_numpy(a).to(dev) for a in vp]
+            vn = {1: 2, 2: 6}[vres]
+            vo = [torch.zeros(n, device=dev) for _ in range(vn)]
+
+            def vstep():
+                for o in vo:
+                    o.zero_()
+                ctx.points_on_points(vcore, vres, o2d.MEM_DEVICE, n, *vd, n, vd[0], vd[1], vd[3], vo[0], vo[1], None,
+                                     *(vo[2:6] if vn == 6 else [None] * 4))
+            vstep()
+            torch.cuda.synchronize()
+            flush.fill_(1.0)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            vsteps = 2
+            e0.record(stream)
+            for _ in range(vsteps):
+                vstep()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            vms = e0.elapsed_time(e1) / vsteps
+            fpp = o2d.flops_per_pair(0, vcore, vres, True)
+            rate = float(n) * float(n) / (vms * 1e-3)
+            variants.append({"what": vname, "core": vcore, "results": vres, "ms_per_step": vms, "value": rate,
+                             "flops_per_pair": fpp, "frac_fp32_peak": fpp * rate / 1e12 / peak_nominal})
+            del vd, vo
+
+    # ---- C1, the reference's own CPU-runnable case, as a latency config: one whole Ralston RK2 convection step
+    #      (2 evaluations of 20k x 20k pairs) through o2d_advect with HOST arrays, next to the CPU reference ----
+    c1 = None
+    if world == 1 and not args.no_variants and args.workload == "c3":
+        cx, cy, cs, cr = W.c1_speedtest(20000)
+        hx = [torch.from_numpy(a.copy()).pin_memory() for a in (cx, cy, cs, cr)]
+        hu = [torch.zeros(20000).pin_memory() for _ in range(2)]
+        def c1_step():
+            hx[0].copy_(torch.from_numpy(cx)); hx[1].copy_(torch.from_numpy(cy))
+            ctx.advect("v2", 2, o2d.MEM_HOST, 20000, hx[0], hx[1], hx[2], hx[3], hu[0], hu[1], dt=0.005)
+        for _ in range(3):
+            c1_step()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            c1_step()
+        gpu_ms = (time.perf_counter() - t0) / 10 * 1e3
+        c1 = {"what": "C1 speedtest20kx10 restated: one RK2 (Ralston) convection step of 20k blobs, V2 core, "
+                      "o2d_advect with host arrays (one upload, both stages on the device, one download)",
+              "gpu_ms_per_step": gpu_ms, "pairs_per_step": 2 * 20000.0 ** 2,
+              "gpu_value": 2 * 20000.0 ** 2 / (gpu_ms * 1e-3), "unit": UNIT}
+        if not args.no_cpu_baseline:
+            import oracle
+            oracle.set_threads()
+            adv = (lambda: oracle.ref("v2").advect(2, cx, cy, cs, cr, 0.005)) if oracle.have_ref() else \
+                  (lambda: oracle.port().advect("v2", 2, cx, cy, cs, cr, 0.005))
+            want = adv()
+            t0 = time.perf_counter()
+            want = adv()
+            cpu_ms = (time.perf_counter() - t0) * 1e3
+            derr = float(np.abs(np.stack([hx[0].numpy() - want[0], hx[1].numpy() - want[1]])).max())
+            c1.update(cpu_ms_per_step=cpu_ms, cpu_value=2 * 20000.0 ** 2 / (cpu_ms * 1e-3), cpu_cores=oracle.host_cores(),
+                      cpu_kind="reference" if oracle.have_ref() else "port", max_abs_position_diff=derr)
 
     # ---- parity spot check + CPU baseline (oracle used as checker / reported baseline only) -------------------
     cpu = None
@@ -391,6 +474,7 @@ def run_ours(args, wl, n1):
                    "parallelism": "single GPU" if world == 1 else f"targets sharded in {world} contiguous blocks, "
                                   "sources all-gathered (NCCL) once per step"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": cnt["launches"],
+        "variants": variants, "c1_step": c1,
         "clocks": clocks, "wall_s_timed_region": wall,
         "frac_fp32_peak_whole_step": flops_pp * value / world / 1e12 / peak_nominal,
     }

@@ -141,6 +141,43 @@ int o2d_zero_vels(o2d_context* ctx, int mem, int n, float* u, float* v, float* w
 int o2d_finalize_vels(o2d_context* ctx, int mem, int n, float* u, float* v, float* w, float* e,
                       double fsx, double fsy);
 
+/* ---- device-resident evaluation and time step (one upload, one download) ------------------ */
+
+/*
+ * Convection::find_vels (reference src/Convection.h:172-223) for one particle collection and
+ * one surface collection acting on one target collection:
+ *     zero_vels -> points_affect_points -> panels_affect_points -> finalize_vels(fs)
+ * i.e. tu,tv (and tq) are OVERWRITTEN with the finished velocities  u = fs + sum/(2 pi)
+ * (vorticity / shear scaled by 1/(2 pi)).  np == 0 means no surface collection; pss == NULL
+ * means vortex-only panels; tr == NULL means inert targets.  results: O2D_VELONLY,
+ * O2D_VELANDVORT or O2D_VELANDSHEAR (panels contribute to tu,tv only, as in the reference,
+ * src/Influence.h:422-614).  With O2D_MEM_HOST the inputs are uploaded once and only the
+ * results come back; the intermediate zero/accumulate/finalize passes never leave the GPU.
+ */
+int o2d_find_vels(o2d_context* ctx, int core, int results, int mem,
+                  int nv, const float* vx, const float* vy, const float* vs, const float* vr,
+                  int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                  const float* pvs, const float* pss,
+                  int nt, const float* tx, const float* ty, const float* tr,
+                  float* tu, float* tv, float* tq, double fsx, double fsy);
+
+/*
+ * One convection step of a Lagrangian particle collection, all stages on the GPU:
+ * Convection::advect_1st (order 1, reference src/Convection.h:277-308), advect_2nd_ralston
+ * (order 2, :314-392) or advect_3rd (order 3, :472-595) with ElementBase::move
+ * (src/ElementBase.h:276-359) between the find_vels evaluations.  x,y are advanced in place;
+ * u,v receive what the reference leaves in the collection's velocity arrays (the weighted
+ * stage velocities for order 2 and 3).  Surface strengths pvs/pss are held fixed over the
+ * step: the reference re-solves its BEM (Eigen, host) and runs clear_inner_layer between
+ * stages, which are outside this library, so for flows with bodies the caller keeps driving
+ * the stages itself through o2d_find_vels; for particle-only flows (np == 0, e.g. the
+ * reference's examples/speedtest20kx10.json) this is the reference's whole convection step.
+ */
+int o2d_advect(o2d_context* ctx, int core, int order, int mem,
+               int n, float* x, float* y, const float* s, const float* r, float* u, float* v,
+               int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+               const float* pvs, const float* pss, double fsx, double fsy, double dt);
+
 /* ---- the reference's existing plugin seam ---------------------------------------------- */
 
 /*

@@ -75,6 +75,9 @@ def load_library() -> C.CDLL:
     lib.o2d_points_vorticity.argtypes = [vp, i, i, vp, vp, vp, vp, i, vp, vp, vp]
     lib.o2d_zero_vels.argtypes = [vp, i, i, vp, vp, vp, vp]
     lib.o2d_finalize_vels.argtypes = [vp, i, i, vp, vp, vp, vp, d, d]
+    lib.o2d_find_vels.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp,
+                                  i, vp, vp, vp, vp, vp, vp, d, d]
+    lib.o2d_advect.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, d, d, d]
     lib.external_vel_solver_f_.restype = C.c_float
     lib.external_vel_solver_f_.argtypes = [C.POINTER(i), vp, vp, vp, vp, C.POINTER(i), vp, vp, vp, vp]
     lib.external_vel_solver_tr_f_.restype = C.c_float
@@ -211,6 +214,22 @@ class Context:
         self._check(self.lib.o2d_finalize_vels(self._h, int(mem), int(n), _ptr(u), _ptr(v), _ptr(w), _ptr(e),
                                                float(fs[0]), float(fs[1])))
 
+    def find_vels(self, core, results, mem, nv, vx, vy, vs, vr, np_, nnodes, nx, ny, idx, pvs, pss,
+                  nt, tx, ty, tr, tu, tv, tq=None, fs=(0.0, 0.0)):
+        core = CORE_ID[core] if isinstance(core, str) else int(core)
+        self._check(self.lib.o2d_find_vels(
+            self._h, core, int(results), int(mem), int(nv), _ptr(vx), _ptr(vy), _ptr(vs), _ptr(vr),
+            int(np_), int(nnodes), _ptr(nx), _ptr(ny), _ptr(idx), _ptr(pvs), _ptr(pss),
+            int(nt), _ptr(tx), _ptr(ty), _ptr(tr), _ptr(tu), _ptr(tv), _ptr(tq), float(fs[0]), float(fs[1])))
+
+    def advect(self, core, order, mem, n, x, y, s, r, u, v, np_=0, nnodes=0, nx=None, ny=None, idx=None,
+               pvs=None, pss=None, fs=(0.0, 0.0), dt=0.0):
+        core = CORE_ID[core] if isinstance(core, str) else int(core)
+        self._check(self.lib.o2d_advect(
+            self._h, core, int(order), int(mem), int(n), _ptr(x), _ptr(y), _ptr(s), _ptr(r), _ptr(u), _ptr(v),
+            int(np_), int(nnodes), _ptr(nx), _ptr(ny), _ptr(idx), _ptr(pvs), _ptr(pss),
+            float(fs[0]), float(fs[1]), float(dt)))
+
     # -- comm
     @staticmethod
     def comm_unique_id() -> bytes:
@@ -240,6 +259,38 @@ class Context:
         self.points_on_points(core, results, MEM_HOST, sx.size, sx, sy, ss, sr, nt, tx, ty, tr,
                               outs[0], outs[1], tq, *g)
         return tuple(outs)
+
+    def find_vels_np(self, core, results, vort, panels, tx, ty, tr=None, fs=(0.0, 0.0)):
+        """vort = (x, y, s, r) or None; panels = (nx, ny, idx, vs, ss|None) or None."""
+        tx, ty, tr = map(_f32, (tx, ty, tr))
+        nt = tx.size
+        vx, vy, vs, vr = map(_f32, vort) if vort is not None else (None,) * 4
+        if panels is not None:
+            nx, ny, pvs, pss = map(_f32, (panels[0], panels[1], panels[3], panels[4]))
+            idx = np.ascontiguousarray(panels[2], dtype=np.uint32)
+            npan, nn = pvs.size, nx.size
+        else:
+            nx = ny = idx = pvs = pss = None
+            npan = nn = 0
+        tu, tv = np.empty(nt, np.float32), np.empty(nt, np.float32)
+        tq = np.empty(nt, np.float32) if results in (VELANDVORT, VELANDSHEAR) else None
+        self.find_vels(core, results, MEM_HOST, 0 if vx is None else vx.size, vx, vy, vs, vr, npan, nn, nx, ny, idx,
+                       pvs, pss, nt, tx, ty, tr, tu, tv, tq, fs)
+        return (tu, tv) if tq is None else (tu, tv, tq)
+
+    def advect_np(self, core, order, x, y, s, r, dt, panels=None, fs=(0.0, 0.0)):
+        x, y = np.array(x, np.float32), np.array(y, np.float32)
+        s, r = map(_f32, (s, r))
+        if panels is not None:
+            nx, ny, pvs, pss = map(_f32, (panels[0], panels[1], panels[3], panels[4]))
+            idx = np.ascontiguousarray(panels[2], dtype=np.uint32)
+            npan, nn = pvs.size, nx.size
+        else:
+            nx = ny = idx = pvs = pss = None
+            npan = nn = 0
+        u, v = np.empty(x.size, np.float32), np.empty(x.size, np.float32)
+        self.advect(core, order, MEM_HOST, x.size, x, y, s, r, u, v, npan, nn, nx, ny, idx, pvs, pss, fs, dt)
+        return x, y, u, v
 
     def panels_on_points_np(self, nx, ny, idx, vs, ss, tx, ty, init=None):
         nx, ny, vs, ss, tx, ty = map(_f32, (nx, ny, vs, ss, tx, ty))

@@ -1,7 +1,6 @@
 // o2d_api.cu -- the C ABI declared in include/omega2d_b200.h: context, device mirrors of
 // host arrays, launch planning, NCCL source all-gather, measurement hooks.
-#include "../../include/omega2d_b200.h"
-#include "o2d_internal.h"
+#include "o2d_context.h"
 
 #include <dlfcn.h>
 #include <algorithm>
@@ -19,39 +18,15 @@ using namespace o2d;
 
 // ---- errors --------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
-static int fail(int code, const char* fmt, ...) {
+int o2d_fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
 }
-#define CU(call)                                                                              \
-  do {                                                                                        \
-    cudaError_t e_ = (call);                                                                  \
-    if (e_ != cudaSuccess)                                                                    \
-      return fail(O2D_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-  } while (0)
-
-// ---- grow-only device buffer -----------------------------------------------------------------------
-struct DevBuf {
-  void* p = nullptr;
-  size_t cap = 0;
-  cudaError_t reserve(size_t bytes) {
-    if (bytes <= cap) return cudaSuccess;
-    if (p) { cudaError_t e = cudaFree(p); if (e != cudaSuccess) return e; p = nullptr; cap = 0; }
-    size_t want = bytes + bytes / 4 + 256;
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e != cudaSuccess) return e;
-    cap = want;
-    return cudaSuccess;
-  }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-  template <class T> T* as() { return reinterpret_cast<T*>(p); }
-};
 
 // ---- NCCL through dlopen (no link-time dependency; single-GPU users never load it) -------------
-typedef struct ncclComm* ncclComm_t;
 struct NcclUid { char internal[128]; };
 struct NcclApi {
   void* handle = nullptr;
@@ -77,34 +52,14 @@ static NcclApi g_nccl;
 static std::mutex g_nccl_mu;
 constexpr int kNcclChar = 0;  // ncclInt8 / ncclChar
 
-// ---- context -----------------------------------------------------------------------------------------
-struct o2d_context {
-  int device = 0;
-  int sm_count = 0;
-  int sm_clock_khz = 0;
-  cudaStream_t own_stream = nullptr;
-  cudaStream_t comm_stream = nullptr;
-  cudaStream_t stream = nullptr;   // stream in use (own or caller's)
-  cudaEvent_t ev_gather = nullptr, ev_pack = nullptr;
-  // scratch
-  DevBuf packed, packed_all, partial, panel_packed;
-  DevBuf hsrc, htgt, hout, hidx;   // device mirrors for O2D_MEM_HOST calls
-  // comm
-  ncclComm_t comm = nullptr;
-  int nranks = 1, rank = 0;
-  // counters
-  long long launches = 0, pair_launches = 0;
-  double pair_ms = 0.0;
-  bool timing = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool, ev_pending;
-};
-
-static int bind_device(o2d_context* c) {
+#define bind_device o2d_bind_device
+#define drain_timing o2d_drain_timing
+int o2d_bind_device(o2d_context* c) {
   CU(cudaSetDevice(c->device));
   return O2D_OK;
 }
 
-static int drain_timing(o2d_context* c) {
+int o2d_drain_timing(o2d_context* c) {
   for (auto& pr : c->ev_pending) {
     CU(cudaEventSynchronize(pr.second));
     float ms = 0.0f;
@@ -116,27 +71,23 @@ static int drain_timing(o2d_context* c) {
   return O2D_OK;
 }
 
-struct PairTimer {   // brackets the dominant kernel launches with events on the launching stream
-  o2d_context* c;
-  std::pair<cudaEvent_t, cudaEvent_t> pr{nullptr, nullptr};
-  explicit PairTimer(o2d_context* ctx) : c(ctx) {
-    if (!c->timing) return;
-    if (c->ev_pending.size() >= 512) drain_timing(c);
-    if (c->ev_pool.empty()) {
-      cudaEventCreate(&pr.first);
-      cudaEventCreate(&pr.second);
-    } else {
-      pr = c->ev_pool.back();
-      c->ev_pool.pop_back();
-    }
-    cudaEventRecord(pr.first, c->stream);
+PairTimer::PairTimer(o2d_context* ctx) : c(ctx) {
+  if (!c->timing) return;
+  if (c->ev_pending.size() >= 512) drain_timing(c);
+  if (c->ev_pool.empty()) {
+    cudaEventCreate(&pr.first);
+    cudaEventCreate(&pr.second);
+  } else {
+    pr = c->ev_pool.back();
+    c->ev_pool.pop_back();
   }
-  ~PairTimer() {
-    if (!c->timing || !pr.first) return;
-    cudaEventRecord(pr.second, c->stream);
-    c->ev_pending.push_back(pr);
-  }
-};
+  cudaEventRecord(pr.first, c->stream);
+}
+PairTimer::~PairTimer() {
+  if (!c->timing || !pr.first) return;
+  cudaEventRecord(pr.second, c->stream);
+  c->ev_pending.push_back(pr);
+}
 
 extern "C" const char* o2d_last_error(void) { return g_err; }
 
@@ -175,7 +126,7 @@ extern "C" int o2d_destroy(o2d_context* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   o2d_comm_destroy(c);
-  for (DevBuf* b : {&c->packed, &c->packed_all, &c->partial, &c->panel_packed, &c->hsrc, &c->htgt, &c->hout, &c->hidx})
+  for (DevBuf* b : {&c->packed, &c->packed_all, &c->partial, &c->panel_packed, &c->hsrc, &c->htgt, &c->hout, &c->hidx, &c->hpan, &c->adv})
     b->release();
   for (auto& pr : c->ev_pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (auto& pr : c->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -224,7 +175,7 @@ static int choose_chunks(int nb, int ntiles, int slots, int max_chunks) {
   return best;
 }
 
-static int res_from_results(int results) {
+int o2d_res_from_results(int results) {
   switch (results) {
     case O2D_VELONLY: return RES_U;
     case O2D_VELANDVORT: return RES_UW;
@@ -261,7 +212,7 @@ static int pp_run_packed(o2d_context* c, int core, int res, const float4* packed
   return O2D_OK;
 }
 
-static int pp_device(o2d_context* c, int core, int res,
+int o2d_pp_device(o2d_context* c, int core, int res,
                      int ns, const float* sx, const float* sy, const float* ss, const float* sr,
                      int nt, const float* tx, const float* ty, const float* tr, const OutPtrs& out) {
   if (ns <= 0 || nt <= 0) return O2D_OK;
@@ -293,35 +244,25 @@ static int pp_device(o2d_context* c, int core, int res,
 }
 
 // ---- host staging helpers ----------------------------------------------------------------------------------
-struct Stager {   // carve float arrays out of one device buffer
-  o2d_context* c;
-  DevBuf* buf;
-  size_t off = 0;
-  Stager(o2d_context* ctx, DevBuf* b) : c(ctx), buf(b) {}
-  float* take(size_t n) {
-    float* p = reinterpret_cast<float*>(reinterpret_cast<char*>(buf->p) + off);
-    off += ((n * sizeof(float) + 255) / 256) * 256;
-    return p;
-  }
-};
-static size_t padded_floats(size_t n) { return ((n * sizeof(float) + 255) / 256) * 256; }
-
-static int h2d(o2d_context* c, float* dst, const float* src, size_t n) {
+int o2d_h2d(o2d_context* c, float* dst, const float* src, size_t n) {
   if (n == 0) return O2D_OK;
   CU(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   return O2D_OK;
 }
-static int d2h(o2d_context* c, float* dst, const float* src, size_t n) {
+int o2d_d2h(o2d_context* c, float* dst, const float* src, size_t n) {
   if (n == 0) return O2D_OK;
   CU(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   return O2D_OK;
 }
+#define h2d o2d_h2d
+#define d2h o2d_d2h
 
-static int check_common(o2d_context* c, int mem) {
+int o2d_check_common(o2d_context* c, int mem) {
   if (!c) return fail(O2D_ERR_INVALID, "ctx is NULL");
   if (mem != O2D_MEM_HOST && mem != O2D_MEM_DEVICE) return fail(O2D_ERR_INVALID, "unknown mem space %d", mem);
   return bind_device(c);
 }
+#define check_common o2d_check_common
 
 // gathers the output pointer list for a results type; returns number of outputs or <0
 static int collect_outputs(int res, float* tu, float* tv, float* tq, float* tux, float* tvx, float* tuy,
@@ -348,7 +289,7 @@ extern "C" int o2d_points_on_points(o2d_context* c, int core, int results, int m
   if (core < 0 || core > 4) return fail(O2D_ERR_INVALID, "unknown core %d", core);
   if (results == O2D_PSIONLY)
     return fail(O2D_ERR_UNSUPPORTED, "Point elements cannot compute streamfunction yet (reference src/Influence.h:60)");
-  const int res = res_from_results(results);
+  const int res = o2d_res_from_results(results);
   if (res < 0) return fail(O2D_ERR_INVALID, "unknown results type %d", results);
   if (ns < 0 || nt < 0) return fail(O2D_ERR_INVALID, "negative count");
   if (ns == 0 || nt == 0) return O2D_OK;
@@ -359,7 +300,7 @@ extern "C" int o2d_points_on_points(o2d_context* c, int core, int results, int m
   OutPtrs o{};
   if (mem == O2D_MEM_DEVICE) {
     for (int k = 0; k < nout; ++k) o.p[k] = outs[k];
-    return pp_device(c, core, res, ns, sx, sy, ss, sr, nt, tx, ty, tr, o);
+    return o2d_pp_device(c, core, res, ns, sx, sy, ss, sr, nt, tx, ty, tr, o);
   }
   // host arrays: mirror on the device, run, copy the accumulated outputs back
   CU(c->hsrc.reserve(4 * padded_floats(ns)));
@@ -377,7 +318,7 @@ extern "C" int o2d_points_on_points(o2d_context* c, int core, int results, int m
     o.p[k] = O.take(nt);
     if ((rc = h2d(c, o.p[k], outs[k], nt))) return rc;
   }
-  if ((rc = pp_device(c, core, res, ns, dsx, dsy, dss, dsr, nt, dtx, dty, dtr, o))) return rc;
+  if ((rc = o2d_pp_device(c, core, res, ns, dsx, dsy, dss, dsr, nt, dtx, dty, dtr, o))) return rc;
   for (int k = 0; k < nout; ++k)
     if ((rc = d2h(c, outs[k], o.p[k], nt))) return rc;
   CU(cudaStreamSynchronize(c->stream));
@@ -394,7 +335,7 @@ extern "C" int o2d_points_vorticity(o2d_context* c, int mem,
   OutPtrs o{};
   if (mem == O2D_MEM_DEVICE) {
     o.p[0] = tw;
-    return pp_device(c, CORE_RM, RES_VORT, ns, sx, sy, ss, sr, nt, tx, ty, nullptr, o);
+    return o2d_pp_device(c, CORE_RM, RES_VORT, ns, sx, sy, ss, sr, nt, tx, ty, nullptr, o);
   }
   CU(c->hsrc.reserve(4 * padded_floats(ns)));
   CU(c->htgt.reserve(3 * padded_floats(nt)));
@@ -408,14 +349,14 @@ extern "C" int o2d_points_vorticity(o2d_context* c, int mem,
       (rc = h2d(c, dsr, sr, ns)) || (rc = h2d(c, dtx, tx, nt)) || (rc = h2d(c, dty, ty, nt)) ||
       (rc = h2d(c, o.p[0], tw, nt)))
     return rc;
-  if ((rc = pp_device(c, CORE_RM, RES_VORT, ns, dsx, dsy, dss, dsr, nt, dtx, dty, nullptr, o))) return rc;
+  if ((rc = o2d_pp_device(c, CORE_RM, RES_VORT, ns, dsx, dsy, dss, dsr, nt, dtx, dty, nullptr, o))) return rc;
   if ((rc = d2h(c, tw, o.p[0], nt))) return rc;
   CU(cudaStreamSynchronize(c->stream));
   return O2D_OK;
 }
 
 // ---- panels ------------------------------------------------------------------------------------------------
-static int panels_on_points_device(o2d_context* c, int np, const float* nx, const float* ny, const uint32_t* idx,
+int o2d_panels_on_points_device(o2d_context* c, int np, const float* nx, const float* ny, const uint32_t* idx,
                                    const float* vs, const float* ss, int nt, const float* tx, const float* ty,
                                    float* tu, float* tv) {
   if (np <= 0 || nt <= 0) return O2D_OK;
@@ -460,7 +401,7 @@ extern "C" int o2d_panels_on_points(o2d_context* c, int mem,
   if (np < 0 || nt < 0 || nnodes < 0) return fail(O2D_ERR_INVALID, "negative count");
   if (np == 0 || nt == 0) return O2D_OK;
   if (!nx || !ny || !idx || !vs || !tx || !ty || !tu || !tv) return fail(O2D_ERR_INVALID, "NULL array");
-  if (mem == O2D_MEM_DEVICE) return panels_on_points_device(c, np, nx, ny, idx, vs, ss, nt, tx, ty, tu, tv);
+  if (mem == O2D_MEM_DEVICE) return o2d_panels_on_points_device(c, np, nx, ny, idx, vs, ss, nt, tx, ty, tu, tv);
   for (int k = 0; k < 2 * np; ++k)
     if (idx[k] >= (uint32_t)nnodes) return fail(O2D_ERR_INVALID, "panel node index %u out of range", idx[k]);
   CU(c->hsrc.reserve(2 * padded_floats(nnodes) + 2 * padded_floats(np)));
@@ -478,14 +419,14 @@ extern "C" int o2d_panels_on_points(o2d_context* c, int mem,
     return rc;
   if (ss && (rc = h2d(c, dss, ss, np))) return rc;
   CU(cudaMemcpyAsync(c->hidx.p, idx, (size_t)2 * np * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-  if ((rc = panels_on_points_device(c, np, dnx, dny, c->hidx.as<uint32_t>(), dvs, dss, nt, dtx, dty, dtu, dtv)))
+  if ((rc = o2d_panels_on_points_device(c, np, dnx, dny, c->hidx.as<uint32_t>(), dvs, dss, nt, dtx, dty, dtu, dtv)))
     return rc;
   if ((rc = d2h(c, tu, dtu, nt)) || (rc = d2h(c, tv, dtv, nt))) return rc;
   CU(cudaStreamSynchronize(c->stream));
   return O2D_OK;
 }
 
-static int points_on_panels_device(o2d_context* c, int ns, const float* sx, const float* sy, const float* ss,
+int o2d_points_on_panels_device(o2d_context* c, int ns, const float* sx, const float* sy, const float* ss,
                                    int np, const float* nx, const float* ny, const uint32_t* idx,
                                    const float* area, float* pu, float* pv) {
   if (ns <= 0 || np <= 0) return O2D_OK;
@@ -528,7 +469,7 @@ extern "C" int o2d_points_on_panels(o2d_context* c, int mem,
   if (ns < 0 || np < 0 || nnodes < 0) return fail(O2D_ERR_INVALID, "negative count");
   if (ns == 0 || np == 0) return O2D_OK;
   if (!sx || !sy || !ss || !nx || !ny || !idx || !area || !pu || !pv) return fail(O2D_ERR_INVALID, "NULL array");
-  if (mem == O2D_MEM_DEVICE) return points_on_panels_device(c, ns, sx, sy, ss, np, nx, ny, idx, area, pu, pv);
+  if (mem == O2D_MEM_DEVICE) return o2d_points_on_panels_device(c, ns, sx, sy, ss, np, nx, ny, idx, area, pu, pv);
   for (int k = 0; k < 2 * np; ++k)
     if (idx[k] >= (uint32_t)nnodes) return fail(O2D_ERR_INVALID, "panel node index %u out of range", idx[k]);
   CU(c->hsrc.reserve(3 * padded_floats(ns)));
@@ -545,7 +486,7 @@ extern "C" int o2d_points_on_panels(o2d_context* c, int mem,
       (rc = h2d(c, dpu, pu, np)) || (rc = h2d(c, dpv, pv, np)))
     return rc;
   CU(cudaMemcpyAsync(c->hidx.p, idx, (size_t)2 * np * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-  if ((rc = points_on_panels_device(c, ns, dsx, dsy, dss, np, dnx, dny, c->hidx.as<uint32_t>(), darea, dpu, dpv)))
+  if ((rc = o2d_points_on_panels_device(c, ns, dsx, dsy, dss, np, dnx, dny, c->hidx.as<uint32_t>(), darea, dpu, dpv)))
     return rc;
   if ((rc = d2h(c, pu, dpu, np)) || (rc = d2h(c, pv, dpv, np))) return rc;
   CU(cudaStreamSynchronize(c->stream));
@@ -844,7 +785,7 @@ extern "C" int o2d_points_on_points_sharded(o2d_context* c, int core, int result
   if (c->nranks > 1 && !c->comm) return fail(O2D_ERR_COMM, "communicator not initialised (o2d_comm_init)");
   if (core < 0 || core > 4) return fail(O2D_ERR_INVALID, "unknown core %d", core);
   if (results == O2D_PSIONLY) return fail(O2D_ERR_UNSUPPORTED, "streamfunction results are not supported");
-  const int res = res_from_results(results);
+  const int res = o2d_res_from_results(results);
   if (res < 0) return fail(O2D_ERR_INVALID, "unknown results type %d", results);
   if (ns_local < 0 || nt < 0 || ns_block <= 0 || ns_local > ns_block)
     return fail(O2D_ERR_INVALID, "bad counts ns_local=%d ns_block=%d nt=%d", ns_local, ns_block, nt);

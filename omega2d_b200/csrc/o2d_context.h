@@ -1,0 +1,101 @@
+// o2d_context.h -- private: the context object and host-side helpers shared by the translation units
+// that implement the C ABI (o2d_api.cu, o2d_substep.cu, o2d_bem.cu).  Not installed.
+#pragma once
+#include "../../include/omega2d_b200.h"
+#include "o2d_internal.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <utility>
+#include <vector>
+
+// ---- errors --------------------------------------------------------------------------------------
+int o2d_fail(int code, const char* fmt, ...);
+#define fail o2d_fail
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(O2D_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// ---- grow-only device buffer -----------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaError_t e = cudaFree(p); if (e != cudaSuccess) return e; p = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) return e;
+    cap = want;
+    return cudaSuccess;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+typedef struct ncclComm* ncclComm_t;
+
+// ---- context -----------------------------------------------------------------------------------------
+struct o2d_context {
+  int device = 0;
+  int sm_count = 0;
+  int sm_clock_khz = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t comm_stream = nullptr;
+  cudaStream_t stream = nullptr;   // stream in use (own or caller's)
+  cudaEvent_t ev_gather = nullptr, ev_pack = nullptr;
+  // scratch
+  DevBuf packed, packed_all, partial, panel_packed;
+  DevBuf hsrc, htgt, hout, hidx, hpan;   // device mirrors for O2D_MEM_HOST calls
+  DevBuf adv;                            // o2d_advect: intermediate Runge-Kutta stages
+  // comm
+  ncclComm_t comm = nullptr;
+  int nranks = 1, rank = 0;
+  // counters
+  long long launches = 0, pair_launches = 0;
+  double pair_ms = 0.0;
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool, ev_pending;
+};
+
+int o2d_bind_device(o2d_context* c);
+int o2d_drain_timing(o2d_context* c);
+
+struct PairTimer {   // brackets the dominant kernel launches with events on the launching stream
+  o2d_context* c;
+  std::pair<cudaEvent_t, cudaEvent_t> pr{nullptr, nullptr};
+  explicit PairTimer(o2d_context* ctx);
+  ~PairTimer();
+};
+
+// ---- host staging helpers ----------------------------------------------------------------------------------
+struct Stager {   // carve float arrays out of one device buffer
+  o2d_context* c;
+  DevBuf* buf;
+  size_t off = 0;
+  Stager(o2d_context* ctx, DevBuf* b) : c(ctx), buf(b) {}
+  float* take(size_t n) {
+    float* p = reinterpret_cast<float*>(reinterpret_cast<char*>(buf->p) + off);
+    off += ((n * sizeof(float) + 255) / 256) * 256;
+    return p;
+  }
+};
+inline size_t padded_floats(size_t n) { return ((n * sizeof(float) + 255) / 256) * 256; }
+int o2d_h2d(o2d_context* c, float* dst, const float* src, size_t n);
+int o2d_d2h(o2d_context* c, float* dst, const float* src, size_t n);
+int o2d_check_common(o2d_context* c, int mem);
+
+// ---- device-pointer workers (all arrays in device memory, asynchronous on c->stream) --------------------
+int o2d_res_from_results(int results);
+int o2d_pp_device(o2d_context* c, int core, int res,
+                  int ns, const float* sx, const float* sy, const float* ss, const float* sr,
+                  int nt, const float* tx, const float* ty, const float* tr, const o2d::OutPtrs& out);
+int o2d_panels_on_points_device(o2d_context* c, int np, const float* nx, const float* ny, const uint32_t* idx,
+                                const float* vs, const float* ss, int nt, const float* tx, const float* ty,
+                                float* tu, float* tv);
+int o2d_points_on_panels_device(o2d_context* c, int ns, const float* sx, const float* sy, const float* ss,
+                                int np, const float* nx, const float* ny, const uint32_t* idx,
+                                const float* area, float* pu, float* pv);

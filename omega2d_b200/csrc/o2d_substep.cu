@@ -1,0 +1,239 @@
+// o2d_substep.cu -- device-resident Runge-Kutta substeps.
+//
+// The reference evaluates velocities 1-3 times per time step (Convection::advect_1st,
+// advect_2nd_ralston, advect_3rd; reference src/Convection.h:277-595), each evaluation being
+// zero_vels -> influence sums over every source collection -> finalize_vels
+// (Convection::find_vels, src/Convection.h:172-223), with ElementBase::move
+// (src/ElementBase.h:276-359) in between.  Called through o2d_points_on_points each evaluation
+// costs a host->device copy of every array and a device->host copy of the results.  The two
+// entry points here keep the particle state on the GPU for a whole evaluation (o2d_find_vels) or a
+// whole time step (o2d_advect): one upload, one download.
+#include "o2d_context.h"
+
+#include <cmath>
+
+using namespace o2d;
+
+namespace {
+
+// ElementBase::move, one weight (src/ElementBase.h:276-296):
+//   x[d][i] += (S)_dt * _wt1 * _u1.u[d][i]     -- (float)dt * double wt -> double; * float u -> double;
+//   the float position is updated through a double sum.  xo may alias xi (in-place move).
+__global__ void __launch_bounds__(256)
+move1_kernel(int n, const float* __restrict__ xi, const float* __restrict__ yi, float* xo, float* yo,
+             const float* __restrict__ u, const float* __restrict__ v, float dt, double wt1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double f = (double)dt * wt1;
+  xo[i] = (float)((double)xi[i] + f * (double)u[i]);
+  yo[i] = (float)((double)yi[i] + f * (double)v[i]);
+}
+
+// ElementBase::move, two / three weights (src/ElementBase.h:299-359):
+//   u[d][i] = _wt1*_u1.u[d][i] + _wt2*_u2.u[d][i] (+ _wt3*_u3.u[d][i])   double math, float store
+//   x[d][i] += (S)_dt * u[d][i]                                            float math
+// u1,v1 belong to the moved collection itself and receive the combined velocity.
+__global__ void __launch_bounds__(256)
+move23_kernel(int n, float* x, float* y, float* u1, float* v1, const float* __restrict__ u2,
+              const float* __restrict__ v2, const float* __restrict__ u3, const float* __restrict__ v3,
+              float dt, double wt1, double wt2, double wt3) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double du = wt1 * (double)u1[i] + wt2 * (double)u2[i];
+  double dv = wt1 * (double)v1[i] + wt2 * (double)v2[i];
+  if (u3 != nullptr) {
+    du += wt3 * (double)u3[i];
+    dv += wt3 * (double)v3[i];
+  }
+  const float fu = (float)du, fv = (float)dv;
+  u1[i] = fu;
+  v1[i] = fv;
+  x[i] = x[i] + dt * fu;
+  y[i] = y[i] + dt * fv;
+}
+
+struct Panels {
+  int np = 0;
+  const float* nx = nullptr;
+  const float* ny = nullptr;
+  const uint32_t* idx = nullptr;
+  const float* vs = nullptr;
+  const float* ss = nullptr;
+};
+
+// Convection::find_vels for one particle collection + one surface collection on one target
+// collection, all in device memory: zero -> particles -> panels -> finalize.
+int find_vels_device(o2d_context* c, int core, int res, int nv, const float* vx, const float* vy, const float* vs,
+                     const float* vr, const Panels& pan, int nt, const float* tx, const float* ty, const float* tr,
+                     float* tu, float* tv, float* tq, double fsx, double fsy) {
+  if (nt <= 0) return O2D_OK;
+  float* w = res == RES_UW ? tq : nullptr;
+  float* e = res == RES_UE ? tq : nullptr;
+  CU(launch_zero(nt, tu, tv, w, e, c->stream));
+  c->launches++;
+  OutPtrs o{};
+  o.p[0] = tu; o.p[1] = tv; o.p[2] = tq;
+  if (int rc = o2d_pp_device(c, core, res, nv, vx, vy, vs, vr, nt, tx, ty, tr, o)) return rc;
+  if (pan.np > 0)
+    if (int rc = o2d_panels_on_points_device(c, pan.np, pan.nx, pan.ny, pan.idx, pan.vs, pan.ss, nt, tx, ty, tu, tv))
+      return rc;
+  CU(launch_finalize(nt, tu, tv, w, e, fsx, fsy, c->stream));
+  c->launches++;
+  return O2D_OK;
+}
+
+// upload the panel description (host -> context mirrors); returns device pointers in `d`
+int stage_panels(o2d_context* c, int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                 const float* vs, const float* ss, Panels* d) {
+  d->np = np;
+  if (np <= 0) return O2D_OK;
+  for (int k = 0; k < 2 * np; ++k)
+    if (idx[k] >= (uint32_t)nnodes) return fail(O2D_ERR_INVALID, "panel node index %u out of range", idx[k]);
+  CU(c->hpan.reserve(2 * padded_floats(nnodes) + 2 * padded_floats(np)));
+  CU(c->hidx.reserve((size_t)2 * np * sizeof(uint32_t)));
+  Stager S(c, &c->hpan);
+  float *dnx = S.take(nnodes), *dny = S.take(nnodes), *dvs = S.take(np), *dss = ss ? S.take(np) : nullptr;
+  int rc;
+  if ((rc = o2d_h2d(c, dnx, nx, nnodes)) || (rc = o2d_h2d(c, dny, ny, nnodes)) || (rc = o2d_h2d(c, dvs, vs, np))) return rc;
+  if (ss && (rc = o2d_h2d(c, dss, ss, np))) return rc;
+  CU(cudaMemcpyAsync(c->hidx.p, idx, (size_t)2 * np * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  d->nx = dnx; d->ny = dny; d->idx = c->hidx.as<uint32_t>(); d->vs = dvs; d->ss = dss;
+  return O2D_OK;
+}
+
+int check_panels(int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx, const float* vs) {
+  if (np < 0 || nnodes < 0) return fail(O2D_ERR_INVALID, "negative count");
+  if (np > 0 && (!nx || !ny || !idx || !vs)) return fail(O2D_ERR_INVALID, "NULL panel array");
+  return O2D_OK;
+}
+
+}  // namespace
+
+extern "C" int o2d_find_vels(o2d_context* c, int core, int results, int mem,
+                             int nv, const float* vx, const float* vy, const float* vs, const float* vr,
+                             int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                             const float* pvs, const float* pss,
+                             int nt, const float* tx, const float* ty, const float* tr,
+                             float* tu, float* tv, float* tq, double fsx, double fsy) {
+  if (int rc = o2d_check_common(c, mem)) return rc;
+  if (core < 0 || core > 4) return fail(O2D_ERR_INVALID, "unknown core %d", core);
+  if (results == O2D_PSIONLY) return fail(O2D_ERR_UNSUPPORTED, "streamfunction results are not supported");
+  if (results == O2D_VELANDGRAD)
+    return fail(O2D_ERR_UNSUPPORTED, "find_vels has no velocity-gradient results (reference src/Convection.h:172-223)");
+  const int res = o2d_res_from_results(results);
+  if (res < 0) return fail(O2D_ERR_INVALID, "unknown results type %d", results);
+  if (nv < 0 || nt < 0) return fail(O2D_ERR_INVALID, "negative count");
+  if (int rc = check_panels(np, nnodes, nx, ny, idx, pvs)) return rc;
+  if (nt == 0) return O2D_OK;
+  if (nv > 0 && (!vx || !vy || !vs || !vr)) return fail(O2D_ERR_INVALID, "NULL particle array");
+  if (!tx || !ty || !tu || !tv) return fail(O2D_ERR_INVALID, "NULL target array");
+  if (res != RES_U && !tq) return fail(O2D_ERR_INVALID, "tq must not be NULL for vorticity/shear results");
+  Panels pan;
+  if (mem == O2D_MEM_DEVICE) {
+    pan.np = np; pan.nx = nx; pan.ny = ny; pan.idx = idx; pan.vs = pvs; pan.ss = pss;
+    return find_vels_device(c, core, res, nv, vx, vy, vs, vr, pan, nt, tx, ty, tr, tu, tv, tq, fsx, fsy);
+  }
+  // host arrays: one upload of sources and target positions, one download of the results
+  // (the outputs are overwritten, so unlike o2d_points_on_points they are not uploaded)
+  CU(c->hsrc.reserve(4 * padded_floats(nv) + 256));
+  CU(c->htgt.reserve(3 * padded_floats(nt)));
+  CU(c->hout.reserve(kMaxOut * padded_floats(nt)));
+  Stager S(c, &c->hsrc), T(c, &c->htgt), O(c, &c->hout);
+  float *dvx = S.take(nv), *dvy = S.take(nv), *dvs = S.take(nv), *dvr = S.take(nv);
+  float *dtx = T.take(nt), *dty = T.take(nt), *dtr = tr ? T.take(nt) : nullptr;
+  float *dtu = O.take(nt), *dtv = O.take(nt), *dtq = tq ? O.take(nt) : nullptr;
+  int rc;
+  if ((rc = o2d_h2d(c, dvx, vx, nv)) || (rc = o2d_h2d(c, dvy, vy, nv)) || (rc = o2d_h2d(c, dvs, vs, nv)) ||
+      (rc = o2d_h2d(c, dvr, vr, nv)) || (rc = o2d_h2d(c, dtx, tx, nt)) || (rc = o2d_h2d(c, dty, ty, nt)))
+    return rc;
+  if (tr && (rc = o2d_h2d(c, dtr, tr, nt))) return rc;
+  if ((rc = stage_panels(c, np, nnodes, nx, ny, idx, pvs, pss, &pan))) return rc;
+  if ((rc = find_vels_device(c, core, res, nv, dvx, dvy, dvs, dvr, pan, nt, dtx, dty, dtr, dtu, dtv, dtq, fsx, fsy)))
+    return rc;
+  if ((rc = o2d_d2h(c, tu, dtu, nt)) || (rc = o2d_d2h(c, tv, dtv, nt))) return rc;
+  if (res != RES_U && (rc = o2d_d2h(c, tq, dtq, nt))) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  return O2D_OK;
+}
+
+// One convection step of a single Lagrangian particle collection, entirely on the device.
+static int advect_device(o2d_context* c, int core, int order, int n, float* x, float* y, const float* s,
+                         const float* r, float* u, float* v, const Panels& pan, double fsx, double fsy, double dt) {
+  const int nb = (n + 255) / 256;
+  const float fdt = (float)dt;   // "(S)_dt" in ElementBase::move
+  auto vels = [&](const float* px, const float* py, float* pu, float* pv) {
+    return find_vels_device(c, core, RES_U, n, px, py, s, r, pan, n, px, py, r, pu, pv, nullptr, fsx, fsy);
+  };
+  int rc;
+  if ((rc = vels(x, y, u, v))) return rc;                       // find_derivs at the initial state
+  if (order == 1) {
+    // advect_1st (src/Convection.h:277-308): elem.move(_time, _dt, 1.0, elem)
+    move1_kernel<<<nb, 256, 0, c->stream>>>(n, x, y, x, y, u, v, fdt, 1.0);
+    CU(cudaGetLastError());
+    c->launches++;
+    return O2D_OK;
+  }
+  // scratch: intermediate positions and velocities (interim_vort / vort1, vort2)
+  CU(c->adv.reserve(8 * padded_floats(n)));
+  Stager A(c, &c->adv);
+  float *x1 = A.take(n), *y1 = A.take(n), *u1 = A.take(n), *v1 = A.take(n);
+  float *x2 = A.take(n), *y2 = A.take(n), *u2 = A.take(n), *v2 = A.take(n);
+  if (order == 2) {
+    // advect_2nd_ralston (src/Convection.h:314-392)
+    const double twothirds = 2.0 / 3.0;
+    move1_kernel<<<nb, 256, 0, c->stream>>>(n, x, y, x1, y1, u, v, (float)(twothirds * dt), 1.0);
+    CU(cudaGetLastError());
+    c->launches++;
+    if ((rc = vels(x1, y1, u1, v1))) return rc;
+    move23_kernel<<<nb, 256, 0, c->stream>>>(n, x, y, u, v, u1, v1, nullptr, nullptr, fdt, 0.25, 0.75, 0.0);
+    CU(cudaGetLastError());
+    c->launches++;
+    return O2D_OK;
+  }
+  // advect_3rd (src/Convection.h:472-595)
+  move1_kernel<<<nb, 256, 0, c->stream>>>(n, x, y, x1, y1, u, v, (float)(0.5 * dt), 1.0);
+  CU(cudaGetLastError());
+  if ((rc = vels(x1, y1, u1, v1))) return rc;
+  move1_kernel<<<nb, 256, 0, c->stream>>>(n, x, y, x2, y2, u1, v1, (float)(0.75 * dt), 1.0);
+  CU(cudaGetLastError());
+  if ((rc = vels(x2, y2, u2, v2))) return rc;
+  move23_kernel<<<nb, 256, 0, c->stream>>>(n, x, y, u, v, u1, v1, u2, v2, fdt, 2.0 / 9.0, 3.0 / 9.0, 4.0 / 9.0);
+  CU(cudaGetLastError());
+  c->launches += 3;
+  return O2D_OK;
+}
+
+extern "C" int o2d_advect(o2d_context* c, int core, int order, int mem,
+                          int n, float* x, float* y, const float* s, const float* r, float* u, float* v,
+                          int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                          const float* pvs, const float* pss, double fsx, double fsy, double dt) {
+  if (int rc = o2d_check_common(c, mem)) return rc;
+  if (core < 0 || core > 4) return fail(O2D_ERR_INVALID, "unknown core %d", core);
+  if (order < 1 || order > 3)
+    return fail(O2D_ERR_INVALID, "Convection integrator orders over 3 unsupported (reference src/Convection.h:259)");
+  if (n < 0) return fail(O2D_ERR_INVALID, "negative count");
+  if (int rc = check_panels(np, nnodes, nx, ny, idx, pvs)) return rc;
+  if (n == 0) return O2D_OK;
+  if (!x || !y || !s || !r || !u || !v) return fail(O2D_ERR_INVALID, "NULL particle array");
+  Panels pan;
+  if (mem == O2D_MEM_DEVICE) {
+    pan.np = np; pan.nx = nx; pan.ny = ny; pan.idx = idx; pan.vs = pvs; pan.ss = pss;
+    return advect_device(c, core, order, n, x, y, s, r, u, v, pan, fsx, fsy, dt);
+  }
+  CU(c->hsrc.reserve(4 * padded_floats(n) + 256));
+  CU(c->hout.reserve(kMaxOut * padded_floats(n)));
+  Stager S(c, &c->hsrc), O(c, &c->hout);
+  float *dx = S.take(n), *dy = S.take(n), *ds = S.take(n), *dr = S.take(n);
+  float *du = O.take(n), *dv = O.take(n);
+  int rc;
+  if ((rc = o2d_h2d(c, dx, x, n)) || (rc = o2d_h2d(c, dy, y, n)) || (rc = o2d_h2d(c, ds, s, n)) ||
+      (rc = o2d_h2d(c, dr, r, n)))
+    return rc;
+  if ((rc = stage_panels(c, np, nnodes, nx, ny, idx, pvs, pss, &pan))) return rc;
+  if ((rc = advect_device(c, core, order, n, dx, dy, ds, dr, du, dv, pan, fsx, fsy, dt))) return rc;
+  if ((rc = o2d_d2h(c, x, dx, n)) || (rc = o2d_d2h(c, y, dy, n)) || (rc = o2d_d2h(c, u, du, n)) ||
+      (rc = o2d_d2h(c, v, dv, n)))
+    return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  return O2D_OK;
+}

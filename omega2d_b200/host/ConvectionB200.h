@@ -9,6 +9,42 @@
 #include <variant>
 #include <vector>
 
+namespace o2d_host {
+// One particle collection (+ at most one surface collection) acting on a Points target: the whole
+// zero -> accumulate -> finalize sequence is ONE library call (o2d_find_vels: one upload, one
+// download) instead of one call -- and one host<->device round trip -- per source collection.
+template <class S>
+bool fused_find_vels(const std::array<double,Dimensions>& _fs, std::vector<Collection>& _vort,
+                     std::vector<Collection>& _bdry, Collection& _targ, const results_t _results) {
+  if (_results != velonly && _results != velandvort && _results != velandshear) return false;
+  if (_vort.size() != 1 || !std::holds_alternative<Points<S>>(_vort[0])) return false;
+  if (_bdry.size() > 1 || (_bdry.size() == 1 && !std::holds_alternative<Surfaces<S>>(_bdry[0]))) return false;
+  if (!std::holds_alternative<Points<S>>(_targ)) return false;
+  const Points<S>& src = std::get<Points<S>>(_vort[0]);
+  Points<S>& targ = std::get<Points<S>>(_targ);
+  const Surfaces<S>* pan = _bdry.empty() ? nullptr : &std::get<Surfaces<S>>(_bdry[0]);
+  const auto& sx = src.get_pos();
+  const auto& tx = targ.get_pos();
+  auto& tu = targ.get_vel();
+  S* tq = nullptr;
+  if (_results == velandvort) tq = targ.get_vort().data();
+  if (_results == velandshear) tq = targ.get_shear().data();
+  // finalize_vels also scales whichever of w/e the collection carries; keep the one not computed here
+  // consistent with the unfused sequence (zeroed, then scaled: stays zero)
+  targ.zero_vels();
+  check(o2d_find_vels(device(), selected_core(), (int)_results, O2D_MEM_HOST,
+                      (int)src.get_n(), sx[0].data(), sx[1].data(), src.get_str().data(), src.get_rad().data(),
+                      pan ? (int)pan->get_npanels() : 0, pan ? (int)pan->get_n() : 0,
+                      pan ? pan->get_pos()[0].data() : nullptr, pan ? pan->get_pos()[1].data() : nullptr,
+                      pan ? pan->get_idx().data() : nullptr, pan ? pan->get_str().data() : nullptr,
+                      (pan && pan->have_src_str()) ? pan->get_src_str().data() : nullptr,
+                      (int)targ.get_n(), tx[0].data(), tx[1].data(), targ.is_inert() ? nullptr : targ.get_rad().data(),
+                      tu[0].data(), tu[1].data(), tq, _fs[0], _fs[1]),
+        "find_vels");
+  return true;
+}
+}  // namespace o2d_host
+
 template <class S, class A>
 void find_vels(const std::array<double,Dimensions>& _fs,
                std::vector<Collection>& _vort, std::vector<Collection>& _bdry, std::vector<Collection>& _targets,
@@ -20,6 +56,7 @@ void find_vels(const std::array<double,Dimensions>& _fs,
     // only for Lagrangian items, or if told to (as when exporting to vtk)
     const move_t tmt = std::visit([=](auto& elem) { return elem.get_movet(); }, targ);
     if (not (_force or tmt == lagrangian)) continue;
+    if (o2d_host::fused_find_vels<S>(_fs, _vort, _bdry, targ, _results)) continue;
     std::visit([=](auto& elem) { elem.zero_vels(); }, targ);
     for (auto& src : _vort) std::visit(visitor, src, targ);
     for (auto& src : _bdry) std::visit(visitor, src, targ);
@@ -27,6 +64,22 @@ void find_vels(const std::array<double,Dimensions>& _fs,
     std::visit([=](auto& elem) { elem.finalize_vels(_fs); }, targ);
   }
   for (auto& src : _bdry) std::visit([=](auto& elem) { elem.add_solved_rot_strengths(-1.0); }, src);
+}
+
+// One convection step of a particle-only flow, all Runge-Kutta stages on the GPU (o2d_advect):
+// Convection::advect_1st / advect_2nd_ralston / advect_3rd (reference src/Convection.h:277-595)
+// for `_vort` = one Lagrangian Points collection and no boundaries (then solve_bem and
+// clear_inner_layer are no-ops).  Positions move in place; the velocity arrays end up holding what
+// the reference leaves there (the weighted stage velocities).
+template <class S>
+void advect_particles(const int _order, const double _dt, const std::array<double,Dimensions>& _fs, Points<S>& _pts) {
+  auto& x = _pts.get_pos();
+  auto& u = _pts.get_vel();
+  o2d_host::check(o2d_advect(o2d_host::device(), o2d_host::selected_core(), _order, O2D_MEM_HOST, (int)_pts.get_n(),
+                             x[0].data(), x[1].data(), _pts.get_str().data(), _pts.get_rad().data(),
+                             u[0].data(), u[1].data(), 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
+                             _fs[0], _fs[1], _dt),
+                  "advect_particles");
 }
 
 template <class S, class A>

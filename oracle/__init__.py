@@ -164,6 +164,44 @@ class Port:
         self.lib.o2d_oracle_finalize_vels(int(u.size), _f(u), _f(v), _f(w), _f(e), float(fs[0]), float(fs[1]))
         return u, v, w, e
 
+    def _panels(self, panels):
+        if panels is None:
+            return 0, 0, None, None, None, None, None
+        nx, ny, pvs, pss = map(_f32, (panels[0], panels[1], panels[3], panels[4]))
+        idx = np.ascontiguousarray(panels[2], dtype=np.uint32)
+        return int(pvs.size), int(nx.size), nx, ny, idx, pvs, pss
+
+    def find_vels(self, core, results, vort, panels, tx, ty, tr=None, fs=(0.0, 0.0)):
+        """Convection::find_vels for one particle + one surface collection on one target set."""
+        tx, ty, tr = map(_f32, (tx, ty, tr))
+        nt = tx.size
+        vx, vy, vs, vr = map(_f32, vort) if vort is not None else (None,) * 4
+        npan, nn, nx, ny, idx, pvs, pss = self._panels(panels)
+        tu, tv = np.zeros(nt, np.float32), np.zeros(nt, np.float32)
+        tq = np.zeros(nt, np.float32) if results in (VELANDVORT, VELANDSHEAR) else None
+        f = self.lib.o2d_oracle_find_vels
+        f.argtypes = [C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp, C.c_int, C.c_int, _fp, _fp, _up, _fp, _fp,
+                      C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, C.c_double, C.c_double]
+        rc = f(CORE_ID[core], int(results), 0 if vx is None else int(vx.size), _f(vx), _f(vy), _f(vs), _f(vr),
+               npan, nn, _f(nx), _f(ny), None if idx is None else _u(idx), _f(pvs), _f(pss),
+               int(nt), _f(tx), _f(ty), _f(tr), _f(tu), _f(tv), _f(tq), float(fs[0]), float(fs[1]))
+        assert rc == 0
+        return (tu, tv) if tq is None else (tu, tv, tq)
+
+    def advect(self, core, order, x, y, s, r, dt, panels=None, fs=(0.0, 0.0)):
+        """One convection step (Euler / Ralston RK2 / RK3) of a particle collection; returns x, y, u, v."""
+        x, y = np.array(x, np.float32), np.array(y, np.float32)
+        s, r = map(_f32, (s, r))
+        npan, nn, nx, ny, idx, pvs, pss = self._panels(panels)
+        u, v = np.zeros(x.size, np.float32), np.zeros(x.size, np.float32)
+        f = self.lib.o2d_oracle_advect
+        f.argtypes = [C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, _fp, _fp, _up,
+                      _fp, _fp, C.c_double, C.c_double, C.c_double]
+        rc = f(CORE_ID[core], int(order), int(x.size), _f(x), _f(y), _f(s), _f(r), _f(u), _f(v),
+               npan, nn, _f(nx), _f(ny), None if idx is None else _u(idx), _f(pvs), _f(pss),
+               float(fs[0]), float(fs[1]), float(dt))
+        assert rc == 0
+        return x, y, u, v
 
 class Ref:
     """The unmodified reference templates for ONE core (oracle/_ref/libo2dref_<core>.so)."""
@@ -250,6 +288,37 @@ class Ref:
         self.lib.o2dref_finalize_vels(int(u.size), _f(u), _f(v), _f(w), _f(e), float(fs[0]), float(fs[1]))
         return u, v, w, e
 
+    _panels = Port._panels
+
+    def find_vels(self, results, vort, panels, tx, ty, tr=None, fs=(0.0, 0.0)):
+        tx, ty, tr = map(_f32, (tx, ty, tr))
+        nt = tx.size
+        vx, vy, vs, vr = map(_f32, vort) if vort is not None else (None,) * 4
+        npan, nn, nx, ny, idx, pvs, pss = self._panels(panels)
+        tu, tv = np.zeros(nt, np.float32), np.zeros(nt, np.float32)
+        tq = np.zeros(nt, np.float32) if results in (VELANDVORT, VELANDSHEAR) else None
+        f = self.lib.o2dref_find_vels
+        f.argtypes = [C.c_int, C.c_int, _fp, _fp, _fp, _fp, C.c_int, C.c_int, _fp, _fp, _up, _fp, _fp,
+                      C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, C.c_double, C.c_double]
+        rc = f(int(results), 0 if vx is None else int(vx.size), _f(vx), _f(vy), _f(vs), _f(vr),
+               npan, nn, _f(nx), _f(ny), None if idx is None else _u(idx), _f(pvs), _f(pss),
+               int(nt), _f(tx), _f(ty), _f(tr), _f(tu), _f(tv), _f(tq), float(fs[0]), float(fs[1]))
+        assert rc == 0
+        return (tu, tv) if tq is None else (tu, tv, tq)
+
+    def advect(self, order, x, y, s, r, dt, panels=None, fs=(0.0, 0.0)):
+        x, y = np.array(x, np.float32), np.array(y, np.float32)
+        s, r = map(_f32, (s, r))
+        npan, nn, nx, ny, idx, pvs, pss = self._panels(panels)
+        u, v = np.zeros(x.size, np.float32), np.zeros(x.size, np.float32)
+        f = self.lib.o2dref_advect
+        f.argtypes = [C.c_int, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, _fp, _fp, _up,
+                      _fp, _fp, C.c_double, C.c_double, C.c_double]
+        rc = f(int(order), int(x.size), _f(x), _f(y), _f(s), _f(r), _f(u), _f(v),
+               npan, nn, _f(nx), _f(ny), None if idx is None else _u(idx), _f(pvs), _f(pss),
+               float(fs[0]), float(fs[1]), float(dt))
+        assert rc == 0
+        return x, y, u, v
 
 def host_cores() -> int:
     """Cores this process may run on (what OpenMP would use by default)."""

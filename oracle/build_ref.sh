@@ -24,7 +24,9 @@ if [ ! -d "$REF/src" ]; then
 fi
 mkdir -p "$OUT"
 MARCH="${O2D_REF_MARCH:--march=x86-64-v3}"
-CXXFLAGS="-std=c++17 -O3 $MARCH -fopenmp -fPIC -DVERBOSE=false -w"
+# -Bsymbolic / -fno-gnu-unique: the five per-core libraries export identically named template
+# instantiations; bind each library's calls to its OWN copies even when several are loaded into one process
+CXXFLAGS="-std=c++17 -O3 $MARCH -fopenmp -fPIC -DVERBOSE=false -w -fno-gnu-unique -Wl,-Bsymbolic"
 STAGE="$(mktemp -d /tmp/o2dref.XXXXXX)"
 trap 'rm -rf "$STAGE"' EXIT
 

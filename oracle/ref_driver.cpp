@@ -255,4 +255,102 @@ int o2dref_finalize_vels(int n, float* u, float* v, float* w, float* e, double f
   return 0;
 }
 
+
+// ---- find_vels and the convection step --------------------------------------------------------
+// Convection.h itself cannot be compiled here (it pulls in BEM.h -> <Eigen/Dense>), so
+// the ORCHESTRATION of Convection::find_vels (src/Convection.h:172-223) and of advect_1st /
+// advect_2nd_ralston / advect_3rd (:277-595) is restated below -- around the reference's own
+// InfluenceVisitor (src/Influence.h:885-900), its own zero_vels / finalize_vels and its own
+// Points::move (src/Points.h:214-252 -> src/ElementBase.h:276-359), operating on the reference's own
+// std::vector<Collection>.  Left out, as in the product entry point: solve_bem (no Eigen) and
+// clear_inner_layer; both are no-ops for a particle-only flow.
+
+static void ref_find_vels(const std::array<double,Dimensions>& fs, std::vector<Collection>& vort,
+                          std::vector<Collection>& bdry, std::vector<Collection>& targets,
+                          const results_t results) {
+  InfluenceVisitor<float,double> visitor = {ResultsType(results), ExecEnv(true, direct, cpu_x86)};
+  for (auto& src : bdry) std::visit([=](auto& elem) { elem.add_solved_rot_strengths(1.0); }, src);
+  for (auto& targ : targets) {
+    std::visit([=](auto& elem) { elem.zero_vels(); }, targ);
+    for (auto& src : vort) std::visit(visitor, src, targ);
+    for (auto& src : bdry) std::visit(visitor, src, targ);
+    std::visit([=](auto& elem) { elem.finalize_vels(fs); }, targ);
+  }
+  for (auto& src : bdry) std::visit([=](auto& elem) { elem.add_solved_rot_strengths(-1.0); }, src);
+}
+
+static void get_xu(Collection& c, int n, float* x, float* y, float* u, float* v) {
+  Points<float>& p = std::get<Points<float>>(c);
+  const auto& px = p.get_pos();
+  const auto& pu = p.get_vel();
+  for (int i = 0; i < n; ++i) {
+    if (x) { x[i] = px[0][i]; y[i] = px[1][i]; }
+    if (u) { u[i] = pu[0][i]; v[i] = pu[1][i]; }
+  }
+}
+
+int o2dref_find_vels(int results,
+                     int nv, const float* vx, const float* vy, const float* vs, const float* vr,
+                     int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                     const float* pvs, const float* pss,
+                     int nt, const float* tx, const float* ty, const float* tr,
+                     float* tu, float* tv, float* tq, double fsx, double fsy) {
+  if (results != velonly && results != velandvort && results != velandshear) return -1;
+  StdoutMute mute;
+  std::vector<Collection> vort, bdry, targ;
+  if (nv > 0) vort.push_back(make_points(nv, vx, vy, vs, vr));
+  if (np > 0) bdry.push_back(make_surfaces(np, nnodes, nx, ny, idx, pvs, pss));
+  targ.push_back(tr ? make_points(nt, tx, ty, tx /*dummy strengths*/, tr) : make_points(nt, tx, ty, nullptr, nullptr));
+  Points<float>& t = std::get<Points<float>>(targ[0]);
+  if (results == velandvort) (void)t.get_vort();    // allocate the optional result arrays
+  if (results == velandshear) (void)t.get_shear();
+  ref_find_vels({fsx, fsy}, vort, bdry, targ, (results_t)results);
+  get_xu(targ[0], nt, nullptr, nullptr, tu, tv);
+  if (results == velandvort) { auto& w = t.get_vort();  for (int i = 0; i < nt; ++i) tq[i] = w[i]; }
+  if (results == velandshear) { auto& e = t.get_shear(); for (int i = 0; i < nt; ++i) tq[i] = e[i]; }
+  return 0;
+}
+
+int o2dref_advect(int order, int n, float* x, float* y, const float* s, const float* r, float* u, float* v,
+                  int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                  const float* pvs, const float* pss, double fsx, double fsy, double dt) {
+  if (order < 1 || order > 3) return -1;
+  StdoutMute mute;
+  const std::array<double,Dimensions> fs = {fsx, fsy};
+  const double time = 0.0;
+  std::vector<Collection> vort, bdry;
+  vort.push_back(make_points(n, x, y, s, r));
+  if (np > 0) bdry.push_back(make_surfaces(np, nnodes, nx, ny, idx, pvs, pss));
+
+  ref_find_vels(fs, vort, bdry, vort, velonly);
+  if (order == 1) {
+    for (auto& coll : vort) std::visit([=](auto& elem) { elem.move(time, dt, 1.0, elem); }, coll);
+  } else if (order == 2) {
+    const double twothirds = 2.0/3.0;
+    std::vector<Collection> interim = vort;
+    for (auto& coll : interim) std::visit([=](auto& elem) { elem.move(time, twothirds*dt, 1.0, elem); }, coll);
+    ref_find_vels(fs, interim, bdry, interim, velonly);
+    Points<float>& p1 = std::get<Points<float>>(vort[0]);
+    Points<float>& p2 = std::get<Points<float>>(interim[0]);
+    p1.move(time, dt, 0.25, p1, 0.75, p2);
+  } else {
+    std::vector<Collection> vort1 = vort;
+    for (auto& coll : vort1) std::visit([=](auto& elem) { elem.move(time, 0.5*dt, 1.0, elem); }, coll);
+    ref_find_vels(fs, vort1, bdry, vort1, velonly);
+    std::vector<Collection> vort2 = vort;
+    {
+      Points<float>& p1 = std::get<Points<float>>(vort1[0]);
+      Points<float>& p2 = std::get<Points<float>>(vort2[0]);
+      p2.move(time, 0.75*dt, 1.0, p1);
+    }
+    ref_find_vels(fs, vort2, bdry, vort2, velonly);
+    Points<float>& p0 = std::get<Points<float>>(vort[0]);
+    Points<float>& p1 = std::get<Points<float>>(vort1[0]);
+    Points<float>& p2 = std::get<Points<float>>(vort2[0]);
+    p0.move(time, dt, 2.0/9.0, p0, 3.0/9.0, p1, 4.0/9.0, p2);
+  }
+  get_xu(vort[0], n, x, y, u, v);
+  return 0;
+}
+
 }  // extern "C"

@@ -79,6 +79,13 @@ int main(int argc, char** argv) {
   dump(f, v2.get_vel()[0]); dump(f, v2.get_vel()[1]); dump(f, v2.get_vort());
   find_vort<float,double>(vort, bdry, fldpt);
   dump(f, std::get<Points<float>>(fldpt[0]).get_vort());
+
+  // one particle-only Ralston RK2 step and one RK3 step, all stages on the device
+  for (int order = 2; order <= 3; ++order) {
+    Points<float> mover = vortons;
+    advect_particles<float>(order, 0.01, fs, mover);
+    dump(f, mover.get_pos()[0]); dump(f, mover.get_pos()[1]); dump(f, mover.get_vel()[0]); dump(f, mover.get_vel()[1]);
+  }
   fclose(f);
   printf("test_find_vels: wrote %s\n", argv[1]);
   return 0;

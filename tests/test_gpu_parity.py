@@ -240,3 +240,76 @@ def test_sharded_single_rank_equals_plain(ctx):
     ctx.points_on_points_sharded("v2", o2d.VELONLY, o2d.MEM_HOST, 30000, 30000, sx, sy, ss, sr,
                                  30000, sx, sy, sr, tu, tv)
     assert W.rel_err((tu, tv), a) < 1e-7
+
+
+# ---- device-resident find_vels / convection step -----------------------------------
+@pytest.fixture(scope="module")
+def gs():
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return np.load(os.path.join(root, "tests", "golden", "ref_golden_substep.npz"))
+
+
+@pytest.mark.parametrize("core", o2d.CORES)
+def test_find_vels_golden(core, ctx, gs):
+    g = gs
+    fs = tuple(g["fs"])
+    vort = (g["x"], g["y"], g["s"], g["r2"])
+    pan = (g["nx"], g["ny"], g["idx"], g["pvs"], g["pss"])
+    for res, key in ((o2d.VELONLY, "u"), (o2d.VELANDVORT, "uw"), (o2d.VELANDSHEAR, "ue")):
+        for tr, tag in ((g["tr"], "blob"), (None, "inert")):
+            got = ctx.find_vels_np(core, res, vort, pan, g["tx"], g["ty"], tr, fs)
+            want = g[f"{core}_fv_{key}_{tag}"]
+            assert W.rel_err(got[:2], (want[0], want[1])) < TOL
+            if len(got) == 3:
+                assert W.rel_err(got[2], want[2]) < TOL
+    got = ctx.find_vels_np(core, o2d.VELONLY, vort, None, g["tx"], g["ty"], g["tr"], fs)
+    assert W.rel_err(got, tuple(g[f"{core}_fv_u_nopanels"])) < TOL
+
+
+@pytest.mark.parametrize("core", o2d.CORES)
+def test_advect_golden(core, ctx, gs):
+    from test_substep_oracle import check_step
+    g = gs
+    fs, dt = tuple(g["fs"]), float(g["dt"])
+    for order in (1, 2, 3):
+        for rk, tag in (("r", ""), ("r2", "_r2")):
+            got = ctx.advect_np(core, order, g["x"], g["y"], g["s"], g[rk], dt, None, fs)
+            check_step(got, g[f"{core}_adv{order}{tag}"], g["x"], g["y"], TOL)
+    pan = (g["nx"], g["ny"], g["idx"], g["pvs"], g["pss"])
+    got = ctx.advect_np(core, 2, g["x"], g["y"], g["s"], g["r2"], dt, pan, fs)
+    check_step(got, g[f"{core}_adv2_panels"], g["x"], g["y"], TOL)
+
+
+def test_advect_c1_speedtest_vs_oracle(ctx, port):
+    """C1 (speedtest20kx10 restated): one RK2 step of 20k uniform-radius blobs, V2 core."""
+    from test_substep_oracle import check_step
+    x, y, s, r = W.c1_speedtest(20000)
+    want = port.advect("v2", 2, x, y, s, r, 0.005)
+    got = ctx.advect_np("v2", 2, x, y, s, r, 0.005)
+    check_step(got, want, x, y, TOL)
+
+
+def test_advect_device_memory_equals_host_path(ctx):
+    import torch
+    x, y, s, r = W.c1_speedtest(5000, seed=3)
+    host = ctx.advect_np("rm", 3, x, y, s, r, 0.01, None, (0.3, 0.0))
+    dev = torch.device("cuda:0")
+    t = [torch.from_numpy(a.copy()).to(dev) for a in (x, y, s, r)]
+    u = torch.empty(5000, device=dev); v = torch.empty(5000, device=dev)
+    ctx.advect("rm", 3, o2d.MEM_DEVICE, 5000, t[0], t[1], t[2], t[3], u, v, fs=(0.3, 0.0), dt=0.01)
+    ctx.synchronize()
+    for a, b in zip(host, (t[0], t[1], u, v)):
+        np.testing.assert_array_equal(a, b.cpu().numpy())
+
+
+def test_find_vels_and_advect_argument_errors(ctx):
+    a = np.ones(4, np.float32)
+    with pytest.raises(o2d.O2DError) as ei:
+        ctx.advect("v2", 4, o2d.MEM_HOST, 4, a.copy(), a.copy(), a, a, a.copy(), a.copy(), dt=0.1)
+    assert ei.value.code == o2d.ERR_INVALID
+    with pytest.raises(o2d.O2DError) as ei:
+        ctx.find_vels("v2", o2d.VELANDGRAD, o2d.MEM_HOST, 4, a, a, a, a, 0, 0, None, None, None, None, None,
+                      4, a, a, a, a.copy(), a.copy())
+    assert ei.value.code == o2d.ERR_UNSUPPORTED
+    ctx.advect("v2", 2, o2d.MEM_HOST, 0, None, None, None, None, None, None, dt=0.1)   # empty set: no-op

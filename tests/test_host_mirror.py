@@ -42,7 +42,8 @@ def test_find_vels_cpp_vs_oracle(tmp_path, port):
         subprocess.run(["bash", os.path.join(ROOT, "omega2d_b200", "host", "build_check.sh")], check=True)
     out = tmp_path / "fv.bin"
     subprocess.run([EXE, str(out), "3000", "143", "500"], check=True, env=dict(os.environ, USE_DEFAULT="1"))
-    (vx, vy, vs_, vr, nx, ny, pvs, pss, area, fx, fy, vu, vv, fu, fv_, bu, bv, wu, wv, ww, fw) = _read_arrays(out)
+    arrs = _read_arrays(out)
+    (vx, vy, vs_, vr, nx, ny, pvs, pss, area, fx, fy, vu, vv, fu, fv_, bu, bv, wu, wv, ww, fw) = arrs[:21]
     npan = pvs.size
     idx = np.empty(2 * npan, np.uint32); idx[0::2] = np.arange(npan); idx[1::2] = (np.arange(npan) + 1) % npan
     fs = (1.0, 0.0)
@@ -81,3 +82,9 @@ def test_find_vels_cpp_vs_oracle(tmp_path, port):
     w = port.points_vorticity(vx, vy, vs_, vr, fx, fy)
     _, _, w, _ = port.finalize_vels(np.zeros_like(w), np.zeros_like(w), w, None, (0.0, 0.0))
     assert W.rel_err(fw, w) < tol
+    # particle-only convection steps (advect_particles -> o2d_advect), orders 2 and 3
+    from test_substep_oracle import check_step
+    for k, order in enumerate((2, 3)):
+        got = arrs[21 + 4 * k: 25 + 4 * k]
+        want = port.advect("v2", order, vx, vy, vs_, vr, 0.01, None, fs)
+        check_step(got, want, vx, vy, tol)
