@@ -178,6 +178,39 @@ int o2d_advect(o2d_context* ctx, int core, int order, int mem,
                int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
                const float* pvs, const float* pss, double fsx, double fsy, double dt);
 
+/* ---- BEM influence coefficients ------------------------------------------------------------ */
+
+/*
+ * Panel-on-panel influence-coefficient block.  Replaces the O(Np^2) loop nest of
+ * panels_on_panels_coeff<S> (reference src/Coefficients.h:155-427; pair kernels kernelu_1vos_0p
+ * src/Kernels.h:413-457 and kernelu_1v_0p :312-354), which solve_bem calls through
+ * CoefficientVisitor for every (source, target) pair of surfaces whenever the geometry changes
+ * (src/BEMHelper.h:165-226).
+ *   source surface: nsrc panels over nsnodes nodes (snx,sny), end nodes sidx[2j],sidx[2j+1],
+ *                   panel lengths sarea (Surfaces::get_area)
+ *   target surface: same, plus unit tangents ttx,tty (Surfaces::get_tang) and normals tnx,tny
+ *                   (Surfaces::get_norm; may be NULL when both_strengths == 0)
+ *   both_strengths: 1 = vortex AND source sheet strengths unknown on both surfaces (what the
+ *                   reference always runs: 2 columns per source panel, 2 rows per target panel);
+ *                   0 = vortex strengths only (1 column / 1 row per panel)
+ *   same_surface:   1 when source and target are the same collection (self influence i == j is
+ *                   set to 1/2 on the diagonal entries, src/Coefficients.h:392-404)
+ *   coeffs:         column-major, leading dimension ld >= rows (rows = (both ? 2 : 1) * ntarg):
+ *                   coeffs[col * ld + row], col = 2j (+1 for the source strength), row = 2i (+1 for
+ *                   the normal condition).  Already scaled by 1/(2 pi), like the reference's return
+ *                   value.  Only the rows x cols block is written, so ld = rows + 1 lets the caller
+ *                   append the reference's augmentation row/column (src/Coefficients.h:431-530)
+ *                   itself -- that part is O(Np) and stays on the host.  With O2D_MEM_DEVICE and
+ *                   both_strengths, ld must be even and coeffs 8-byte aligned.
+ */
+int o2d_panels_on_panels_coeff(o2d_context* ctx, int mem,
+                               int nsrc, int nsnodes, const float* snx, const float* sny,
+                               const uint32_t* sidx, const float* sarea,
+                               int ntarg, int ntnodes, const float* tnx_nodes, const float* tny_nodes,
+                               const uint32_t* tidx, const float* tarea,
+                               const float* ttx, const float* tty, const float* tnx, const float* tny,
+                               int both_strengths, int same_surface, long long ld, float* coeffs);
+
 /* ---- the reference's existing plugin seam ---------------------------------------------- */
 
 /*

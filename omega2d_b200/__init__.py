@@ -78,6 +78,8 @@ def load_library() -> C.CDLL:
     lib.o2d_find_vels.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp,
                                   i, vp, vp, vp, vp, vp, vp, d, d]
     lib.o2d_advect.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, d, d, d]
+    lib.o2d_panels_on_panels_coeff.argtypes = [vp, i, i, i, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp,
+                                               i, i, C.c_longlong, vp]
     lib.external_vel_solver_f_.restype = C.c_float
     lib.external_vel_solver_f_.argtypes = [C.POINTER(i), vp, vp, vp, vp, C.POINTER(i), vp, vp, vp, vp]
     lib.external_vel_solver_tr_f_.restype = C.c_float
@@ -230,6 +232,13 @@ class Context:
             int(np_), int(nnodes), _ptr(nx), _ptr(ny), _ptr(idx), _ptr(pvs), _ptr(pss),
             float(fs[0]), float(fs[1]), float(dt)))
 
+    def panels_on_panels_coeff(self, mem, nsrc, nsnodes, snx, sny, sidx, sarea, ntarg, ntnodes, tnx, tny, tidx,
+                               tarea, ttx, tty, tnnx, tnny, both, same, ld, coeffs):
+        self._check(self.lib.o2d_panels_on_panels_coeff(
+            self._h, int(mem), int(nsrc), int(nsnodes), _ptr(snx), _ptr(sny), _ptr(sidx), _ptr(sarea),
+            int(ntarg), int(ntnodes), _ptr(tnx), _ptr(tny), _ptr(tidx), _ptr(tarea), _ptr(ttx), _ptr(tty),
+            _ptr(tnnx), _ptr(tnny), int(both), int(same), int(ld), _ptr(coeffs)))
+
     # -- comm
     @staticmethod
     def comm_unique_id() -> bytes:
@@ -291,6 +300,20 @@ class Context:
         u, v = np.empty(x.size, np.float32), np.empty(x.size, np.float32)
         self.advect(core, order, MEM_HOST, x.size, x, y, s, r, u, v, npan, nn, nx, ny, idx, pvs, pss, fs, dt)
         return x, y, u, v
+
+    def panels_on_panels_coeff_np(self, src, sarea, targ, tbases, both=True, same=False, ld=None):
+        """src/targ = (nx, ny, idx); tbases = (ttx, tty, tnx, tny, tarea).  Returns (cols, ld) float32."""
+        snx, sny = map(_f32, src[:2]); sidx = np.ascontiguousarray(src[2], dtype=np.uint32)
+        tnx, tny = map(_f32, targ[:2]); tidx = np.ascontiguousarray(targ[2], dtype=np.uint32)
+        ttx, tty, tnnx, tnny, tarea = map(_f32, tbases)
+        sarea = _f32(sarea)
+        ns, nt = sidx.size // 2, tidx.size // 2
+        unk = 2 if both else 1
+        ld = unk * nt if ld is None else int(ld)
+        c = np.zeros((unk * ns, ld), np.float32)
+        self.panels_on_panels_coeff(MEM_HOST, ns, snx.size, snx, sny, sidx, sarea, nt, tnx.size, tnx, tny, tidx, tarea,
+                                    ttx, tty, tnnx, tnny, both, same, ld, c)
+        return c
 
     def panels_on_points_np(self, nx, ny, idx, vs, ss, tx, ty, init=None):
         nx, ny, vs, ss, tx, ty = map(_f32, (nx, ny, vs, ss, tx, ty))

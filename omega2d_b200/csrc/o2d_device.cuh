@@ -62,6 +62,60 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// ---- constant-strength panel pair (shared by o2d_panels.cu and o2d_bem.cu) ----------------------------
+// atan2(c, d) on the FMA pipe + one MUFU.RCP (libm's atan2f is a ~60-instruction branchy sequence).
+// Octant reduction to |x| <= tan(pi/8) (x = min/max, or (min-max)/(min+max) with a pi/4 offset), then
+// the Cephes atanf minimax polynomial; measured <= 2.3e-7 relative to float64 atan2 over all
+// quadrants, the same as libm's float result, and relative (not absolute) for small angles.
+__device__ __forceinline__ float atan2_fast(float c, float d) {
+  const float ax = fabsf(d), ay = fabsf(c);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const bool big = mn > 0.41421356f * mx;
+  const float nn = big ? mn - mx : mn;
+  const float dd = big ? mn + mx : mx;
+  const float x = nn * mufu_rcp(dd);
+  const float z = x * x;
+  float p = fmaf(8.05374449538e-2f, z, -1.38776856032e-1f);
+  p = fmaf(p, z, 1.99777106478e-1f);
+  p = fmaf(p, z, -3.33329491539e-1f);
+  p = fmaf(p * z, x, x);
+  float r = big ? p + 0.78539816339744831f : p;
+  r = ay > ax ? 1.57079632679489662f - r : r;
+  r = d < 0.0f ? 3.14159265358979324f - r : r;
+  r = mx == 0.0f ? 0.0f : r;                    // atan2(0,0) = 0, as std::atan2
+  return copysignf(r, c);
+}
+
+// ustar, vstar of one (panel, point) pair.  vstar = 0.5 log(rij2/rij12) = atanh(z) with
+// z = (rij2 - rij12)/(rij2 + rij12): the numerator is formed without cancellation from the panel
+// vector, and for |z| < 0.2 (point further than ~2.5 panel lengths away: almost every pair) the odd
+// series z + z^3/3 + ... + z^9/9 is exact to 6e-8 relative.  Closer in, two MUFU.LG2 are accurate
+// enough in relative terms because |vstar| >= 0.2; that path is skipped warp-wide when no lane needs it.
+__device__ __forceinline__ void panel_pair(float x0, float y0, float px, float py, float tx, float ty,
+                                           float& ustar, float& vstar) {
+  const float dx0 = tx - x0;
+  const float dy0 = ty - y0;
+  const float dx1 = dx0 - px;
+  const float dy1 = dy0 - py;
+  const float rij2 = fmaf(dx0, dx0, dy0 * dy0);
+  const float rij12 = fmaf(dx1, dx1, dy1 * dy1);
+  const float cross = fmaf(py, dx0, -(px * dy0));
+  const float dot = fmaf(dx0, dx1, dy0 * dy1);
+  ustar = atan2_fast(cross, dot);
+  const float num = fmaf(px, dx0 + dx1, py * (dy0 + dy1));   // = rij2 - rij12
+  const float z = num * mufu_rcp(rij2 + rij12);
+  const float w = z * z;
+  float q = fmaf(1.0f / 9.0f, w, 1.0f / 7.0f);
+  q = fmaf(q, w, 0.2f);
+  q = fmaf(q, w, 1.0f / 3.0f);
+  vstar = fmaf(z * w, q, z);
+  const bool near = !(fabsf(z) < 0.2f);          // also catches NaN (point on a node)
+  if (__any_sync(__activemask(), near)) {
+    const float lg = 0.34657359027997264f * (mufu_lg2(rij2) - mufu_lg2(rij12));   // 0.5 ln 2
+    vstar = near ? lg : vstar;
+  }
+}
+
 // ---- radius terms ----------------------------------------------------------------------------
 // Per-element radius term the cores add to the distance term: r^2 for RM/EXP/WL, r^4 for V2,
 // r^6 for V3, formed with the reference's own float products (s2 = sr*sr; s2*s2; s2*s2*s2,

@@ -12,8 +12,8 @@
 // Here the same two numbers are formed without the cancellations of that form:
 //     ustar = atan2(cross, dot),  cross = py*dx0 - px*dy0 (= dx1*dy0 - dy1*dx0),  dot = dx0*dx1 + dy0*dy1
 //       -- the angle between the two node vectors; the +-pi wrap is implicit;
-//     vstar = 0.5 log1p((rij2-rij12)/rij12),  rij2-rij12 = px*(dx0+dx1) + py*(dy0+dy1)
-// with (px,py) = node1 - node0.  The rotation and the strengths are linear, so they are hoisted:
+//     vstar = atanh((rij2-rij12)/(rij2+rij12)),  rij2-rij12 = px*(dx0+dx1) + py*(dy0+dy1)
+// with (px,py) = node1 - node0; both evaluated with FMA-pipe polynomials (atan2_fast, panel_pair below).  The rotation and the strengths are linear, so they are hoisted:
 //   panels_on_points:  u += ustar*a - vstar*b ,  v += ustar*b + vstar*a
 //                      a = (vs*px + ss*py)/len , b = (vs*py - ss*px)/len   (per panel, packed once)
 //   points_on_panels:  A1 = sum s_j ustar_j , A2 = sum s_j vstar_j   (per panel), then
@@ -23,20 +23,6 @@
 #include "o2d_internal.h"
 
 namespace o2d {
-
-__device__ __forceinline__ void panel_pair(float x0, float y0, float px, float py, float tx, float ty,
-                                           float& ustar, float& vstar) {
-  const float dx0 = tx - x0;
-  const float dy0 = ty - y0;
-  const float dx1 = dx0 - px;
-  const float dy1 = dy0 - py;
-  const float rij12 = fmaf(dx1, dx1, dy1 * dy1);
-  const float cross = fmaf(py, dx0, -(px * dy0));
-  const float dot = fmaf(dx0, dx1, dy0 * dy1);
-  ustar = atan2f(cross, dot);
-  const float num = fmaf(px, dx0 + dx1, py * (dy0 + dy1));
-  vstar = 0.5f * log1pf(num / rij12);
-}
 
 // ---- packing: gather node coordinates through idx once (the reference gathers per pair,
 // src/Influence.h:561-562) ---------------------------------------------------------------------------

@@ -48,14 +48,29 @@ public:
   const Vector<S>& get_src_str() const { return *ps[1]; }
   Vector<S>&       get_src_str()       { return *ps[1]; }
 
-  // panel length and unit tangent (reference src/Surfaces.h:699-711)
+  // basis vectors and boundary conditions the BEM assembly reads (reference src/Surfaces.h:237-262)
+  const std::array<Vector<S>,Dimensions>& get_tang() const { return b[0]; }
+  const std::array<Vector<S>,Dimensions>& get_norm() const { return b[1]; }
+  const Vector<S>& get_norm_bcs() const { return nbc; }
+  Vector<S>&       get_norm_bcs()       { return nbc; }
+  Int num_unknowns_per_panel() const { return 2; }     // source_str_is_unknown is always true (src/Surfaces.h:69)
+  bool is_augmented() const { return false; }          // no attached Body in this layer (src/Surfaces.h:304-313)
+  S get_vol() const { return S(0); }
+
+  // panel length, unit tangent and normal (reference src/Surfaces.h:682-726); the normal points into
+  // the fluid, to the left when walking from node 0 to node 1
   void compute_bases() {
     area.resize(np);
+    nbc.assign(np, S(0));
+    for (size_t i = 0; i < Dimensions; ++i) for (size_t j = 0; j < Dimensions; ++j) b[i][j].resize(np);
     for (size_t i = 0; i < np; ++i) {
       const size_t id0 = idx[2*i], id1 = idx[2*i+1];
-      const S dx = this->x[0][id1] - this->x[0][id0];
-      const S dy = this->x[1][id1] - this->x[1][id0];
-      area[i] = std::sqrt(dx*dx + dy*dy);
+      S x1[2] = { this->x[0][id1] - this->x[0][id0], this->x[1][id1] - this->x[1][id0] };
+      const S base = std::sqrt(x1[0]*x1[0] + x1[1]*x1[1]);
+      for (size_t j = 0; j < Dimensions; ++j) x1[j] *= (1.0/base);
+      area[i] = base;
+      b[0][0][i] = x1[0];  b[0][1][i] = x1[1];
+      b[1][0][i] = -x1[1]; b[1][1][i] = x1[0];
     }
   }
 
@@ -88,6 +103,8 @@ protected:
   size_t np;
   std::vector<Int> idx;
   Vector<S> area;
+  std::array<std::array<Vector<S>,Dimensions>,Dimensions> b;   // b[0] tangent, b[1] normal
+  Vector<S> nbc;                                               // normal-velocity boundary condition per panel
   std::array<Vector<S>,Dimensions> pu;
   std::array<std::optional<Vector<S>>,2> ps;
 };

@@ -21,6 +21,9 @@ if [ -d "$REF/src" ]; then
 #define OMEGA2D_REFERENCE_HEADERS
 #include "InfluenceB200.h"
 #include "ConvectionB200.h"
+#include "CoefficientsB200.h"
+Vector<float> coeff_block(Collection& a, Collection& b) { return std::visit(CoefficientVisitor<float>(), a, b); }
+std::vector<float> rhs_block(Collection& a) { return std::visit(RHSVisitor<float>(), a); }
 void instantiate(std::vector<Collection>& a, std::vector<Collection>& b, std::vector<Collection>& c) {
   find_vels<float,double>({0.0, 0.0}, a, b, c, velandvort, true);
   find_vort<float,double>(a, b, c);
@@ -28,5 +31,5 @@ void instantiate(std::vector<Collection>& a, std::vector<Collection>& b, std::ve
 CPP
   g++ -std=c++17 -fsyntax-only -w -I"$REF/src" -I"$REF/lib" -I"$REF/lib/tinyexpr" -I"$REF/lib/tinyxml2" -I"$HERE" \
       "$ROOT/build/ref_containers_check.cpp"
-  echo "InfluenceB200.h compiles against the reference's own Points/Surfaces/Volumes/Collection"
+  echo "InfluenceB200.h compiles against the reference's own Points/Surfaces/Volumes/Collection (InfluenceVisitor, CoefficientVisitor, RHSVisitor)"
 fi

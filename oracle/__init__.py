@@ -202,6 +202,44 @@ class Port:
                float(fs[0]), float(fs[1]), float(dt))
         assert rc == 0
         return x, y, u, v
+    def panel_bases(self, nx, ny, idx):
+        """Surfaces::compute_bases: returns ttx, tty, tnx, tny, area."""
+        nx, ny = map(_f32, (nx, ny))
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        n = idx.size // 2
+        out = [np.zeros(n, np.float32) for _ in range(5)]
+        self.lib.o2d_oracle_panel_bases(int(n), _f(nx), _f(ny), _u(idx), *[_f(o) for o in out])
+        return tuple(out)
+
+    def panels_on_panels_coeff(self, src, targ=None, both=True, ld=None):
+        """src/targ = (nx, ny, idx); targ None = same surface.  Returns the column-major block as a
+        (cols, ld) array (row index fastest), like the reference's Vector<S>."""
+        same = targ is None
+        targ = src if same else targ
+        snx, sny = map(_f32, src[:2]); sidx = np.ascontiguousarray(src[2], dtype=np.uint32)
+        tnx, tny = map(_f32, targ[:2]); tidx = np.ascontiguousarray(targ[2], dtype=np.uint32)
+        ns, nt = sidx.size // 2, tidx.size // 2
+        ttx, tty, tnx_, tny_, ta = self.panel_bases(tnx, tny, tidx)
+        sa = self.panel_bases(snx, sny, sidx)[4]
+        unk = 2 if both else 1
+        ld = unk * nt if ld is None else int(ld)
+        c = np.zeros((unk * ns, ld), np.float32)
+        f = self.lib.o2d_oracle_panels_on_panels_coeff
+        f.argtypes = [C.c_int, _fp, _fp, _up, _fp, C.c_int, _fp, _fp, _up, _fp, _fp, _fp, _fp, _fp,
+                      C.c_int, C.c_int, C.c_longlong, _fp]
+        rc = f(ns, _f(snx), _f(sny), _u(sidx), _f(sa), nt, _f(tnx), _f(tny), _u(tidx), _f(ta),
+               _f(ttx), _f(tty), _f(tnx_), _f(tny_), int(both), int(same), ld, _f(c))
+        assert rc == 0
+        return c
+
+    def vels_to_rhs_panels(self, nx, ny, idx, pu, pv, nbc=None, nunk=2):
+        ttx, tty, tnx, tny, _ = self.panel_bases(nx, ny, idx)
+        pu, pv = map(_f32, (pu, pv))
+        nbc = np.zeros(pu.size, np.float32) if nbc is None else _f32(nbc)
+        rhs = np.zeros(nunk * pu.size, np.float32)
+        self.lib.o2d_oracle_vels_to_rhs_panels(int(pu.size), int(nunk), _f(pu), _f(pv), _f(ttx), _f(tty), _f(tnx),
+                                               _f(tny), _f(nbc), _f(rhs))
+        return rhs
 
 class Ref:
     """The unmodified reference templates for ONE core (oracle/_ref/libo2dref_<core>.so)."""
@@ -319,6 +357,42 @@ class Ref:
                float(fs[0]), float(fs[1]), float(dt))
         assert rc == 0
         return x, y, u, v
+    def panels_on_panels_coeff(self, src, targ=None):
+        """The reference's own panels_on_panels_coeff<float> (always both strengths).  Returns
+        (coeffs as (2*ns, 2*nt) array, (ttx, tty, tnx, tny, tarea), sarea)."""
+        same = targ is None
+        targ = src if same else targ
+        snx, sny = map(_f32, src[:2]); sidx = np.ascontiguousarray(src[2], dtype=np.uint32)
+        tnx, tny = map(_f32, targ[:2]); tidx = np.ascontiguousarray(targ[2], dtype=np.uint32)
+        ns, nt = sidx.size // 2, tidx.size // 2
+        c = np.zeros((2 * ns, 2 * nt), np.float32)
+        bases = [np.zeros(nt, np.float32) for _ in range(5)]
+        sa = np.zeros(ns, np.float32)
+        rc = self.lib.o2dref_panels_on_panels_coeff(ns, int(snx.size), _f(snx), _f(sny), _u(sidx),
+                                                    nt, int(tnx.size), _f(tnx), _f(tny), _u(tidx), int(same),
+                                                    _f(c), *[_f(b) for b in bases], _f(sa))
+        assert rc == 0
+        return c, tuple(bases), sa
+
+    def panels_on_panels_coeff_vortex(self, src, targ, bases, sa, same):
+        snx, sny = map(_f32, src[:2]); sidx = np.ascontiguousarray(src[2], dtype=np.uint32)
+        tnx, tny = map(_f32, targ[:2]); tidx = np.ascontiguousarray(targ[2], dtype=np.uint32)
+        ns, nt = sidx.size // 2, tidx.size // 2
+        c = np.zeros((ns, nt), np.float32)
+        rc = self.lib.o2dref_panels_on_panels_coeff_vortex(ns, _f(snx), _f(sny), _u(sidx), _f(_f32(sa)),
+                                                           nt, _f(tnx), _f(tny), _u(tidx), _f(_f32(bases[4])),
+                                                           _f(_f32(bases[0])), _f(_f32(bases[1])), int(same), _f(c))
+        assert rc == 0
+        return c
+
+    def vels_to_rhs_panels(self, nx, ny, idx, pu, pv, nbc=None):
+        nx, ny, pu, pv, nbc = map(_f32, (nx, ny, pu, pv, nbc))
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        rhs = np.zeros(2 * pu.size, np.float32)
+        n = self.lib.o2dref_vels_to_rhs_panels(int(pu.size), int(nx.size), _f(nx), _f(ny), _u(idx), _f(pu), _f(pv),
+                                               _f(nbc), _f(rhs))
+        assert n == rhs.size
+        return rhs
 
 def host_cores() -> int:
     """Cores this process may run on (what OpenMP would use by default)."""

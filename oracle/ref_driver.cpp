@@ -26,6 +26,8 @@
 #include "Collection.h"
 #include "Influence.h"
 #include "InfluenceVort.h"
+#include "Coefficients.h"
+#include "RHS.h"
 
 #include <cstdio>
 #include <cstring>
@@ -351,6 +353,85 @@ int o2dref_advect(int order, int n, float* x, float* y, const float* s, const fl
   }
   get_xu(vort[0], n, x, y, u, v);
   return 0;
+}
+
+
+// ---- BEM coefficients -----------------------------------------------------------------------------
+// reference panels_on_panels_coeff<float> (src/Coefficients.h:155-573) called on the reference's
+// own Surfaces.  same != 0: one surface acting on itself (self-influence diagonal).  The reference
+// always has source_str_is_unknown == true (src/Surfaces.h:69), so this is the 2x2-per-pair layout;
+// returns the unaugmented block (no Body attached), column-major with ld = 2*ntarg.
+// Also returns the bases the reference derived (tangent, normal, length; compute_bases, :682-726).
+int o2dref_panels_on_panels_coeff(int nsrc, int nsnodes, const float* snx, const float* sny, const uint32_t* sidx,
+                                  int ntarg, int ntnodes, const float* tnx, const float* tny, const uint32_t* tidx,
+                                  int same, float* coeffs, float* tt_x, float* tt_y, float* tn_x, float* tn_y,
+                                  float* tarea, float* sarea) {
+  StdoutMute mute;
+  std::vector<float> zs((size_t)nsrc, 0.0f), zt((size_t)ntarg, 0.0f);
+  Surfaces<float> src = make_surfaces(nsrc, nsnodes, snx, sny, sidx, zs.data(), zs.data());
+  Vector<float> c;
+  if (same) {
+    c = panels_on_panels_coeff<float>(src, src);
+  } else {
+    Surfaces<float> targ = make_surfaces(ntarg, ntnodes, tnx, tny, tidx, zt.data(), zt.data());
+    c = panels_on_panels_coeff<float>(src, targ);
+  }
+  Surfaces<float> tcopy = same ? src : make_surfaces(ntarg, ntnodes, tnx, tny, tidx, zt.data(), zt.data());
+  if (c.size() != (size_t)4 * nsrc * ntarg) return -1;
+  for (size_t k = 0; k < c.size(); ++k) coeffs[k] = c[k];
+  const auto& tt = tcopy.get_tang();
+  const auto& tn = tcopy.get_norm();
+  const auto& ta = tcopy.get_area();
+  for (int i = 0; i < ntarg; ++i) { tt_x[i] = tt[0][i]; tt_y[i] = tt[1][i]; tn_x[i] = tn[0][i]; tn_y[i] = tn[1][i]; tarea[i] = ta[i]; }
+  const auto& sa = src.get_area();
+  for (int j = 0; j < nsrc; ++j) sarea[j] = sa[j];
+  return 0;
+}
+
+// vortex-strength-only layout: the reference's else-branch (src/Coefficients.h:372-389) is unreachable
+// through Surfaces (source_str_is_unknown is always true), so its loop is restated here around the
+// reference's own kernelu_1v_0p<float,float> (src/Kernels.h:312-354).
+int o2dref_panels_on_panels_coeff_vortex(int nsrc, const float* snx, const float* sny, const uint32_t* sidx,
+                                         const float* sa,
+                                         int ntarg, const float* tnx, const float* tny, const uint32_t* tidx,
+                                         const float* ta, const float* ttx, const float* tty, int same, float* coeffs) {
+  const float fac = 1.0 / (2.0 * M_PI);
+  #pragma omp parallel for
+  for (int32_t j = 0; j < (int32_t)nsrc; j++) {
+    const float sx0 = snx[sidx[2*j]], sy0 = sny[sidx[2*j]], sx1 = snx[sidx[2*j+1]], sy1 = sny[sidx[2*j+1]];
+    for (int i = 0; i < ntarg; i++) {
+      const float tx0 = tnx[tidx[2*i]], ty0 = tny[tidx[2*i]], tx1 = tnx[tidx[2*i+1]], ty1 = tny[tidx[2*i+1]];
+      const float xi = 0.5 * (tx1 + tx0);
+      const float yi = 0.5 * (ty1 + ty0);
+      float vortu, vortv;
+      kernelu_1v_0p<float,float>(sx0, sy0, sx1, sy1, 1.0, xi, yi, &vortu, &vortv);
+      float col = vortu*ttx[i] + vortv*tty[i];
+      kernelu_1v_0p<float,float>(tx0, ty0, tx1, ty1, 1.0, 0.5*(sx0+sx1), 0.5*(sy0+sy1), &vortu, &vortv);
+      col -= (vortu*ttx[i] + vortv*tty[i]) * (sa[j]/ta[i]);
+      col *= 0.5;
+      if (same && i == j) col = M_PI;
+      coeffs[(size_t)j * ntarg + i] = col * fac;
+    }
+  }
+  return 0;
+}
+
+// reference vels_to_rhs_panels<float> (src/RHS.h:54-116) on a reactive Surfaces whose panel velocities
+// and normal boundary condition are given; returns the number of rhs entries (2 per panel)
+int o2dref_vels_to_rhs_panels(int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                              const float* pu, const float* pv, const float* nbc, float* rhs) {
+  StdoutMute mute;
+  std::vector<float> px(2 * (size_t)nnodes);
+  for (int i = 0; i < nnodes; ++i) { px[2*i] = nx[i]; px[2*i+1] = ny[i]; }
+  std::vector<Int> pidx(idx, idx + 2 * (size_t)np);
+  std::vector<float> val(2 * (size_t)np, 0.0f);
+  for (int i = 0; i < np; ++i) val[2*i+1] = nbc ? nbc[i] : 0.0f;
+  Surfaces<float> s(ElementPacket<float>(px, pidx, val, (size_t)np, 1), reactive, fixed, nullptr);
+  auto& u = s.get_vel();
+  for (int i = 0; i < np; ++i) { u[0][i] = pu[i]; u[1][i] = pv[i]; }
+  std::vector<float> r = vels_to_rhs_panels<float>(s);
+  for (size_t k = 0; k < r.size(); ++k) rhs[k] = r[k];
+  return (int)r.size();
 }
 
 }  // extern "C"

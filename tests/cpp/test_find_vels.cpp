@@ -3,6 +3,7 @@
 // runs find_vels / find_vort through InfluenceVisitor -> C ABI -> CUDA, and dumps inputs and
 // results as raw float32 for tests/test_host_mirror.py to check against the oracle.
 #include "ConvectionB200.h"
+#include "CoefficientsB200.h"
 
 #include <cstdio>
 #include <cstdint>
@@ -85,6 +86,16 @@ int main(int argc, char** argv) {
     Points<float> mover = vortons;
     advect_particles<float>(order, 0.01, fs, mover);
     dump(f, mover.get_pos()[0]); dump(f, mover.get_pos()[1]); dump(f, mover.get_vel()[0]); dump(f, mover.get_vel()[1]);
+  }
+
+  // BEM block of the body on itself through CoefficientVisitor, and the RHS from the panel velocities
+  // found above (what solve_bem does, reference src/BEMHelper.h:96-112,190-200)
+  {
+    Vector<float> coeffs = std::visit(CoefficientVisitor<float>(), bdry[0], bdry[0]);
+    dump(f, coeffs);
+    Surfaces<float>& bb = std::get<Surfaces<float>>(bdry[0]);
+    for (size_t i = 0; i < np; ++i) bb.get_norm_bcs()[i] = 0.01f * (float)(i % 7);
+    dump(f, std::visit(RHSVisitor<float>(), bdry[0]));
   }
   fclose(f);
   printf("test_find_vels: wrote %s\n", argv[1]);

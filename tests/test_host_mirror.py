@@ -88,3 +88,11 @@ def test_find_vels_cpp_vs_oracle(tmp_path, port):
         got = arrs[21 + 4 * k: 25 + 4 * k]
         want = port.advect("v2", order, vx, vy, vs_, vr, 0.01, None, fs)
         check_step(got, want, vx, vy, tol)
+    # BEM coefficient block (CoefficientVisitor -> o2d_panels_on_panels_coeff) and RHS (RHSVisitor)
+    from test_bem_oracle import mat_err
+    coeffs, rhs = arrs[29], arrs[30]
+    want = port.panels_on_panels_coeff((nx, ny, idx))
+    assert coeffs.size == want.size
+    assert mat_err(coeffs.reshape(want.shape), want) < tol
+    nbc = (0.01 * (np.arange(npan) % 7)).astype(np.float32)
+    np.testing.assert_allclose(rhs, port.vels_to_rhs_panels(nx, ny, idx, bu, bv, nbc), atol=2e-6)
