@@ -211,6 +211,27 @@ int o2d_panels_on_panels_coeff(o2d_context* ctx, int mem,
                                const float* ttx, const float* tty, const float* tnx, const float* tny,
                                int both_strengths, int same_surface, long long ld, float* coeffs);
 
+/* ---- clear_inner_layer ------------------------------------------------------------------ */
+
+/*
+ * Push particles out of the innermost layer around a body.  Replaces clear_inner_panp2<S> with
+ * _method == 1 (reference src/Reflect.h:490-733; closest-point kernel panel_point_distance
+ * :108-170) as called by clear_inner_layer<S> (:735-768) for one Surfaces boundary and one
+ * Lagrangian Points collection -- what Convection does after every move of every Runge-Kutta stage
+ * (src/Convection.h:303-307) with cutoff_mult = 0.5/sqrt(2 pi) and ips = the inter-particle spacing.
+ *   panels: np panels over nnodes nodes (nx,ny), idx, unit panel normals snx,sny (Surfaces::get_norm)
+ *   points: n positions tx,ty, moved in place (strengths and radii are not touched by method 1)
+ *   num_moved: if non-NULL receives the number of pushes (the reference's "pushed N particles")
+ * Every particle closer than cutoff_mult*ips (minus 0.001 ips) to the surface along the mean normal of
+ * its closest panel(s)/node(s) is moved onto that layer; the search repeats for moved particles until
+ * none moves (corners).  method 0 (strength cropping with the diffusion cut tables) returns
+ * O2D_ERR_UNSUPPORTED.
+ */
+int o2d_clear_inner_layer(o2d_context* ctx, int method, int mem,
+                          int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                          const float* snx, const float* sny,
+                          int n, float* tx, float* ty, float cutoff_mult, float ips, long long* num_moved);
+
 /* ---- the reference's existing plugin seam ---------------------------------------------- */
 
 /*

@@ -80,6 +80,8 @@ def load_library() -> C.CDLL:
     lib.o2d_advect.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, d, d, d]
     lib.o2d_panels_on_panels_coeff.argtypes = [vp, i, i, i, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp,
                                                i, i, C.c_longlong, vp]
+    lib.o2d_clear_inner_layer.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp, i, vp, vp, C.c_float, C.c_float,
+                                          C.POINTER(C.c_longlong)]
     lib.external_vel_solver_f_.restype = C.c_float
     lib.external_vel_solver_f_.argtypes = [C.POINTER(i), vp, vp, vp, vp, C.POINTER(i), vp, vp, vp, vp]
     lib.external_vel_solver_tr_f_.restype = C.c_float
@@ -239,6 +241,14 @@ class Context:
             int(ntarg), int(ntnodes), _ptr(tnx), _ptr(tny), _ptr(tidx), _ptr(tarea), _ptr(ttx), _ptr(tty),
             _ptr(tnnx), _ptr(tnny), int(both), int(same), int(ld), _ptr(coeffs)))
 
+    def clear_inner_layer(self, method, mem, np_, nnodes, nx, ny, idx, snx, sny, n, tx, ty, cutoff_mult, ips,
+                          want_count=True):
+        moved = C.c_longlong(0)
+        self._check(self.lib.o2d_clear_inner_layer(
+            self._h, int(method), int(mem), int(np_), int(nnodes), _ptr(nx), _ptr(ny), _ptr(idx), _ptr(snx), _ptr(sny),
+            int(n), _ptr(tx), _ptr(ty), float(cutoff_mult), float(ips), C.byref(moved) if want_count else None))
+        return moved.value
+
     # -- comm
     @staticmethod
     def comm_unique_id() -> bytes:
@@ -314,6 +324,13 @@ class Context:
         self.panels_on_panels_coeff(MEM_HOST, ns, snx.size, snx, sny, sidx, sarea, nt, tnx.size, tnx, tny, tidx, tarea,
                                     ttx, tty, tnnx, tnny, both, same, ld, c)
         return c
+
+    def clear_inner_layer_np(self, nx, ny, idx, snx, sny, x, y, cutoff_mult, ips):
+        nx, ny, snx, sny = map(_f32, (nx, ny, snx, sny))
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        x, y = np.array(x, np.float32), np.array(y, np.float32)
+        moved = self.clear_inner_layer(1, MEM_HOST, snx.size, nx.size, nx, ny, idx, snx, sny, x.size, x, y, cutoff_mult, ips)
+        return x, y, moved
 
     def panels_on_points_np(self, nx, ny, idx, vs, ss, tx, ty, init=None):
         nx, ny, vs, ss, tx, ty = map(_f32, (nx, ny, vs, ss, tx, ty))

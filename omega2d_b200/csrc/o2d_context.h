@@ -51,6 +51,7 @@ struct o2d_context {
   DevBuf packed, packed_all, partial, panel_packed;
   DevBuf hsrc, htgt, hout, hidx, hpan;   // device mirrors for O2D_MEM_HOST calls
   DevBuf adv;                            // o2d_advect: intermediate Runge-Kutta stages
+  DevBuf counter;                        // small device-side counters
   DevBuf coef;                           // o2d_panels_on_panels_coeff: device copy of the matrix block
   // comm
   ncclComm_t comm = nullptr;

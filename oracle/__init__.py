@@ -240,6 +240,18 @@ class Port:
         self.lib.o2d_oracle_vels_to_rhs_panels(int(pu.size), int(nunk), _f(pu), _f(pv), _f(ttx), _f(tty), _f(tnx),
                                                _f(tny), _f(nbc), _f(rhs))
         return rhs
+    def clear_inner_layer(self, nx, ny, idx, x, y, cutoff_factor, ips, max_iter=1000):
+        """clear_inner_layer, method 1 (push).  Returns new x, y and the number of pushes."""
+        nx, ny = map(_f32, (nx, ny)); idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        _, _, snx, sny, _ = self.panel_bases(nx, ny, idx)
+        x, y = np.array(x, np.float32), np.array(y, np.float32)
+        f = self.lib.o2d_oracle_clear_inner_layer
+        f.restype = C.c_longlong
+        f.argtypes = [C.c_int, C.c_int, _fp, _fp, _up, _fp, _fp, C.c_int, _fp, _fp, C.c_float, C.c_float, C.c_int]
+        moved = f(int(idx.size // 2), int(nx.size), _f(nx), _f(ny), _u(idx), _f(snx), _f(sny), int(x.size), _f(x), _f(y),
+                  float(cutoff_factor), float(ips), int(max_iter))
+        assert moved >= 0
+        return x, y, int(moved)
 
 class Ref:
     """The unmodified reference templates for ONE core (oracle/_ref/libo2dref_<core>.so)."""
@@ -393,6 +405,17 @@ class Ref:
                                                _f(nbc), _f(rhs))
         assert n == rhs.size
         return rhs
+    def clear_inner_layer(self, nx, ny, idx, x, y, cutoff_factor, ips, s=None, r=None, method=1):
+        nx, ny = map(_f32, (nx, ny)); idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        x, y = np.array(x, np.float32), np.array(y, np.float32)
+        s = None if s is None else np.array(s, np.float32)
+        r = None if r is None else _f32(r)
+        f = self.lib.o2dref_clear_inner_layer
+        f.argtypes = [C.c_int, C.c_int, C.c_int, _fp, _fp, _up, C.c_int, _fp, _fp, _fp, _fp, C.c_float, C.c_float]
+        rc = f(int(method), int(idx.size // 2), int(nx.size), _f(nx), _f(ny), _u(idx), int(x.size), _f(x), _f(y), _f(s), _f(r),
+               float(cutoff_factor), float(ips))
+        assert rc == 0
+        return (x, y) if s is None else (x, y, s)
 
 def host_cores() -> int:
     """Cores this process may run on (what OpenMP would use by default)."""

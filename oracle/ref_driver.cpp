@@ -28,6 +28,7 @@
 #include "InfluenceVort.h"
 #include "Coefficients.h"
 #include "RHS.h"
+#include "Reflect.h"
 
 #include <cstdio>
 #include <cstring>
@@ -432,6 +433,35 @@ int o2dref_vels_to_rhs_panels(int np, int nnodes, const float* nx, const float* 
   std::vector<float> r = vels_to_rhs_panels<float>(s);
   for (size_t k = 0; k < r.size(); ++k) rhs[k] = r[k];
   return (int)r.size();
+}
+
+
+// ---- clear_inner_layer ------------------------------------------------------------------------------
+// reference clear_inner_layer<float> (src/Reflect.h:735-768 -> clear_inner_panp2 :490-733) on the
+// reference's own Collections: one Surfaces boundary, one Lagrangian Points collection (blobs with
+// radius r, or inert field points when s == NULL).  method 1 = push (what Convection calls after
+// every move, src/Convection.h:303-307), method 0 = crop with the cut tables.  Positions (and, for
+// method 0, strengths) are returned in place.
+int o2dref_clear_inner_layer(int method, int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                             int n, float* x, float* y, float* s, const float* r, float cutoff_factor, float ips) {
+  StdoutMute mute;
+  std::vector<float> z((size_t)np, 0.0f);
+  std::vector<Collection> bdry, vort;
+  bdry.push_back(make_surfaces(np, nnodes, nx, ny, idx, z.data(), z.data()));
+  if (s) {
+    vort.push_back(make_points(n, x, y, s, r));
+  } else {
+    std::vector<float> px(2 * (size_t)n);
+    for (int i = 0; i < n; ++i) { px[2*i] = x[i]; px[2*i+1] = y[i]; }
+    vort.push_back(Points<float>(ElementPacket<float>(px, std::vector<Int>(), std::vector<float>(), (size_t)n, 0),
+                                 inert, lagrangian, nullptr, 0.0f));
+  }
+  clear_inner_layer<float>(method, bdry, vort, cutoff_factor, ips);
+  Points<float>& p = std::get<Points<float>>(vort[0]);
+  const auto& px = p.get_pos();
+  for (int i = 0; i < n; ++i) { x[i] = px[0][i]; y[i] = px[1][i]; }
+  if (s) { const auto& ps = p.get_str(); for (int i = 0; i < n; ++i) s[i] = ps[i]; }
+  return 0;
 }
 
 }  // extern "C"

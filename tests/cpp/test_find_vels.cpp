@@ -4,6 +4,7 @@
 // results as raw float32 for tests/test_host_mirror.py to check against the oracle.
 #include "ConvectionB200.h"
 #include "CoefficientsB200.h"
+#include "ReflectB200.h"
 
 #include <cstdio>
 #include <cstdint>
@@ -96,6 +97,17 @@ int main(int argc, char** argv) {
     Surfaces<float>& bb = std::get<Surfaces<float>>(bdry[0]);
     for (size_t i = 0; i < np; ++i) bb.get_norm_bcs()[i] = 0.01f * (float)(i % 7);
     dump(f, std::visit(RHSVisitor<float>(), bdry[0]));
+  }
+  // clear_inner_layer (push) on a copy of the particles shifted towards the body
+  {
+    std::vector<Collection> near;
+    Points<float> shifted = vortons;
+    for (size_t i = 0; i < nv; ++i) { shifted.get_pos()[0][i] *= 0.9f; shifted.get_pos()[1][i] *= 0.9f; }
+    dump(f, shifted.get_pos()[0]); dump(f, shifted.get_pos()[1]);
+    near.push_back(shifted);
+    clear_inner_layer<float>(1, bdry, near, 0.5f / std::sqrt(2.0f * 3.14159265f), 0.02191f);
+    const Points<float>& out = std::get<Points<float>>(near[0]);
+    dump(f, out.get_pos()[0]); dump(f, out.get_pos()[1]);
   }
   fclose(f);
   printf("test_find_vels: wrote %s\n", argv[1]);

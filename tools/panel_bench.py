@@ -56,3 +56,22 @@ for npan in (143, 5000, 20000):
     print(f"panels_on_panels_coeff np={npan:6d}  {ms:9.3f} ms  {pairs/(ms*1e-3):.3e} pairs/s  matrix {16*pairs/1e9:.2f} GB  "
           f"store {16*pairs/(ms*1e-3)/1e9:.0f} GB/s", flush=True)
     del c
+
+# clear_inner_layer (push), device memory
+for npan, n in ((143, 1 << 20), (20000, 1 << 20)):
+    nx, ny, idx, _, _ = W.circle_panels(npan, radius=0.5)
+    i0, i1 = idx[0::2], idx[1::2]
+    px, py = nx[i1] - nx[i0], ny[i1] - ny[i0]
+    area = np.hypot(px, py)
+    snx, sny = (-py / area).astype(np.float32), (px / area).astype(np.float32)
+    rng = np.random.default_rng(1)
+    x = rng.uniform(-1, 1, n).astype(np.float32); y = rng.uniform(-1, 1, n).astype(np.float32)
+    d = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (nx, ny, snx, sny)]
+    didx = torch.from_numpy(idx.astype(np.int32)).to(dev)
+    for rep in range(2):
+        dx = torch.from_numpy(x).to(dev); dy = torch.from_numpy(y).to(dev)
+        ctx.synchronize(); ctx.reset_counters(); ctx.enable_timing(True)
+        moved = ctx.clear_inner_layer(1, o2d.MEM_DEVICE, npan, npan, d[0], d[1], didx, d[2], d[3], n, dx, dy, 0.2, 0.02)
+        ctx.synchronize(); cnt = ctx.counters(); ctx.enable_timing(False)
+    ms = cnt["pair_ms"]
+    print(f"clear_inner_layer np={npan:6d} n={n:8d}  {ms:9.3f} ms  moved {moved}  {npan*float(n)/(ms*1e-3):.3e} panel-point tests/s (first sweep)", flush=True)
