@@ -51,6 +51,9 @@ WORKLOADS = {
                    desc="C3: 1M-particle Gaussian vortex blob, Rosenhead-Moore core, velocity + gradient (kernelug_0v_0b)"),
     "c1": dict(n=20_000, core="v2", results=1, blob=True,
                desc="C1: speedtest20kx10 restated, 20k blobs, Vatistas-2 core, velocity"),
+    "c4": dict(n=4_194_304, core="rm", results=1, blob=True, panels=(4, 5000), scaling="strong",
+               desc="C4: 4M-particle Gaussian blob + 20k panels (4 closed circles of 5000), Rosenhead-Moore core: one "
+                    "find_vels on the particles (zero, particles-on-particles, panels-on-particles, finalize)"),
     "c5": dict(n=16_777_216, core="wl", results=1, blob=True,
                desc="C5: 16M-particle Gaussian blob, Winckelmans-Leonard core, velocity"),
     "v2": dict(n=1_000_000, core="v2", results=1, blob=True,
@@ -84,7 +87,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--n", type=int, default=0, help="override the particle count at 1 GPU")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="default: the workload's own (weak, except c4: strong)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of one cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -95,12 +99,18 @@ def parse_args():
 # ---------------------------------------------------------------------------------------------
 # CPU side: the reference's own loop (oracle/_ref) or, if that was never built, the C port
 # ---------------------------------------------------------------------------------------------
-def cpu_checker(core: str):
+def cpu_checker(core: str, panels=None):
+    """The CPU arm: the reference's own loops (oracle/_ref) or, if that was never built, the C port.  With
+    panels the call is the whole find_vels (zero, particles, panels, finalize), else points_affect_points."""
     import oracle
     if oracle.have_ref():
         r = oracle.ref(core)
+        if panels is not None:
+            return "reference", (lambda res, sx, sy, ss, sr, tx, ty, tr: r.find_vels(res, (sx, sy, ss, sr), panels, tx, ty, tr))
         return "reference", (lambda res, *a: r.points_on_points(res, *a))
     p = oracle.port()
+    if panels is not None:
+        return "port", (lambda res, sx, sy, ss, sr, tx, ty, tr: p.find_vels(core, res, (sx, sy, ss, sr), panels, tx, ty, tr))
     return "port", (lambda res, *a: p.points_on_points(core, res, *a))
 
 
@@ -108,7 +118,8 @@ def cpu_sample(wl, parts, seconds: float):
     """Time the CPU path on a strided target subset against ALL sources (onbody's ntskip
     method, reference extern/onbody/src/main2dvort.cpp:116-133), sized for ~`seconds`."""
     import oracle
-    kind, fn = cpu_checker(wl["core"])
+    panels = W.multi_circle_panels(*wl["panels"]) if wl.get("panels") else None
+    kind, fn = cpu_checker(wl["core"], panels)
     oracle.set_threads()          # torchrun exports OMP_NUM_THREADS=1; use every host core
     sx, sy, ss, sr = parts
     n = sx.size
@@ -129,6 +140,10 @@ def cpu_sample(wl, parts, seconds: float):
     return kind, run, count
 
 
+def sources_per_target(wl, n):
+    return n + (wl["panels"][0] * wl["panels"][1] if wl.get("panels") else 0)
+
+
 def run_reference_arm(args, wl, n):
     """--impl reference: the reference's OpenMP direct sum on the host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -143,7 +158,7 @@ def run_reference_arm(args, wl, n):
         dt, _, _ = run(count)
         times.append(dt)
     total = sum(times)
-    value = args.steps * count * n / total
+    value = args.steps * count * sources_per_target(wl, n) / total
     import oracle
     cores = oracle.host_cores()
     line = {
@@ -263,11 +278,22 @@ def run_ours(args, wl, n1):
     outs = [torch.zeros(max(nloc, 1), device=dev) for _ in range(nout)]
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)   # > 126 MB L2
 
+    pan = None
+    if wl.get("panels"):
+        pnx, pny, pidx, pvs, pss = W.multi_circle_panels(*wl["panels"])
+        pan = dict(np=pvs.size, nn=pnx.size, host=(pnx, pny, pidx, pvs, pss),
+                   dev=[torch.from_numpy(a).to(dev) for a in (pnx, pny, pidx.astype(np.int32), pvs, pss)])
+
     def step_device():
         tq = outs[2] if nout == 3 else None
         g = outs[2:6] if nout == 6 else [None] * 4
         tr = d[3] if wl["blob"] else None
-        if world == 1:
+        if pan is not None:
+            p = pan["dev"]
+            ctx.find_vels_sharded(core, results, o2d.MEM_DEVICE, nloc, nblock, d[0], d[1], d[2], d[3],
+                                  pan["np"], pan["nn"], p[0], p[1], p[2], p[3], p[4],
+                                  nloc, d[0], d[1], tr, outs[0], outs[1], tq, (0.0, 0.0))
+        elif world == 1:
             ctx.points_on_points(core, results, o2d.MEM_DEVICE, nloc, d[0], d[1], d[2], d[3],
                                  nloc, d[0], d[1], tr, outs[0], outs[1], tq, *g)
         else:
@@ -310,7 +336,7 @@ def run_ours(args, wl, n1):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max, pair_ms_max = float(t[0]), float(t[1])
-    pairs_per_step = float(n) * float(n)
+    pairs_per_step = float(n) * float(n) + (float(n) * pan["np"] if pan is not None else 0.0)
     value = args.steps * pairs_per_step / (ms_max * 1e-3)
 
     # ---- result check on a few targets (oracle as checker only) --------------------------------------
@@ -326,7 +352,12 @@ def run_ours(args, wl, n1):
             tq = houts[2] if nout == 3 else None
             g = houts[2:6] if nout == 6 else [None] * 4
             tr = h[3] if wl["blob"] else None
-            if world == 1:
+            if pan is not None:
+                p = pan["host"]
+                ctx.find_vels_sharded(core, results, o2d.MEM_HOST, nloc, nblock, h[0], h[1], h[2], h[3],
+                                      pan["np"], pan["nn"], p[0], p[1], p[2], p[3], p[4],
+                                      nloc, h[0], h[1], tr, houts[0], houts[1], tq, (0.0, 0.0))
+            elif world == 1:
                 ctx.points_on_points(core, results, o2d.MEM_HOST, nloc, h[0], h[1], h[2], h[3],
                                      nloc, h[0], h[1], tr, houts[0], houts[1], tq, *g)
             else:
@@ -348,10 +379,13 @@ def run_ours(args, wl, n1):
         if world > 1:
             dist.all_reduce(et, op=dist.ReduceOp.MAX)
         h2d = 4 * (4 * nloc + (3 if wl["blob"] else 2) * nloc + nout * nloc) * world
+        if pan is not None:   # find_vels overwrites its outputs (no upload of them); panels go up on every rank
+            h2d = (4 * (4 * nloc + (3 if wl["blob"] else 2) * nloc) + 4 * (2 * pan["nn"] + 4 * pan["np"])) * world
         d2h = 4 * nout * nloc * world
         e2e = {"value": e_steps * pairs_per_step / float(et[0]), "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e_steps,
-               "api": "o2d_points_on_points[_sharded](O2D_MEM_HOST) on pinned host arrays"}
+               "api": ("o2d_find_vels_sharded" if pan is not None else "o2d_points_on_points[_sharded]") +
+                      "(O2D_MEM_HOST) on pinned host arrays"}
         # host path and device path must agree bit for bit
         if not np.array_equal(houts[0][:nloc].numpy(), u):
             bad = int((houts[0][:nloc].numpy() != u).sum())
@@ -366,8 +400,9 @@ def run_ours(args, wl, n1):
     # ---- roofline of the dominant kernel -----------------------------------------------------------------
     flops_pp = o2d.flops_per_pair(0, core, results, wl["blob"])
     pairs_rank0 = float(nloc) * float(n)
+    panel_flops = 47.0 * float(nloc) * pan["np"] if pan is not None else 0.0   # flopsu_1vs_0p (src/Kernels.h:362)
     kern_s = pair_ms_max * 1e-3 / args.steps          # pair-sum kernel time per step (max over ranks)
-    achieved = flops_pp * pairs_rank0 / kern_s / 1e12 if kern_s > 0 else 0.0
+    achieved = (flops_pp * pairs_rank0 + panel_flops) / kern_s / 1e12 if kern_s > 0 else 0.0
     peak_nominal = info["fp32_peak_tflops"]
     ffma = ctx.measure_fp32_peak(False)
     ffma2 = ctx.measure_fp32_peak(True)
@@ -461,7 +496,7 @@ def run_ours(args, wl, n1):
         scale = np.sqrt(u.astype(np.float64) ** 2 + v.astype(np.float64) ** 2).max()
         err = np.sqrt((u[sub] - ref_out[0]).astype(np.float64) ** 2 + (v[sub] - ref_out[1]).astype(np.float64) ** 2).max() / scale
         import oracle
-        cpu = {"value": count * n / dt, "unit": UNIT, "cores": oracle.host_cores(), "kind": kind,
+        cpu = {"value": count * sources_per_target(wl, n) / dt, "unit": UNIT, "cores": oracle.host_cores(), "kind": kind,
                "sample": f"{count} strided targets x all {n} sources, one call, OpenMP on all host cores, USE_VC off",
                "seconds": dt, "max_rel_err_gpu_vs_cpu": float(err), "tolerance": 1e-5}
 
@@ -476,7 +511,8 @@ def run_ours(args, wl, n1):
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": cnt["launches"],
         "variants": variants, "c1_step": c1,
         "clocks": clocks, "wall_s_timed_region": wall,
-        "frac_fp32_peak_whole_step": flops_pp * value / world / 1e12 / peak_nominal,
+        "frac_fp32_peak_whole_step": (flops_pp * float(n) * float(n) + panel_flops * world) / (ms_max * 1e-3 / args.steps)
+                                     / world / 1e12 / peak_nominal,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -487,6 +523,8 @@ def run_ours(args, wl, n1):
 def main():
     args = parse_args()
     wl = WORKLOADS[args.workload]
+    if args.scaling is None:
+        args.scaling = wl.get("scaling", "weak")
     n1 = args.n or wl["n"]
     if args.impl == "reference":
         world = int(os.environ.get("WORLD_SIZE", "1"))

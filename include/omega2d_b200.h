@@ -275,6 +275,30 @@ int o2d_points_on_points_sharded(o2d_context* ctx, int core, int results, int me
                                  float* tu, float* tv, float* tq,
                                  float* tux, float* tvx, float* tuy, float* tvy);
 
+/*
+ * Sharded Convection::find_vels: o2d_find_vels with the particle collection split over the ranks
+ * like o2d_points_on_points_sharded (this rank's block of nv_local <= nv_block particles is
+ * all-gathered once), the surface collection replicated on every rank (it is small: 24 B per
+ * panel) and this rank's nt targets.  tu,tv,tq are overwritten with the finished velocities.
+ */
+int o2d_find_vels_sharded(o2d_context* ctx, int core, int results, int mem,
+                          int nv_local, int nv_block,
+                          const float* vx, const float* vy, const float* vs, const float* vr,
+                          int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                          const float* pvs, const float* pss,
+                          int nt, const float* tx, const float* ty, const float* tr,
+                          float* tu, float* tv, float* tq, double fsx, double fsy);
+/*
+ * Sharded points_affect_panels (the BEM right-hand side, reference src/BEMHelper.h:96-99): every
+ * rank holds ns_local particles of the global set and ALL np panels; the per-panel reciprocity
+ * sums are added over the ranks with one ncclAllReduce of 2*np float64 and folded into pu,pv
+ * ("pu -= sum/area") identically on every rank.
+ */
+int o2d_points_on_panels_sharded(o2d_context* ctx, int mem,
+                                 int ns_local, const float* sx, const float* sy, const float* ss,
+                                 int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                                 const float* area, float* pu, float* pv);
+
 /* ---- measurement hooks (used by bench.py; no effect on results) ------------------------- */
 
 /* Reference ("algorithmic") flops per pair, from the reference's own counters

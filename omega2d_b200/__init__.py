@@ -82,6 +82,9 @@ def load_library() -> C.CDLL:
                                                i, i, C.c_longlong, vp]
     lib.o2d_clear_inner_layer.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp, i, vp, vp, C.c_float, C.c_float,
                                           C.POINTER(C.c_longlong)]
+    lib.o2d_find_vels_sharded.argtypes = [vp, i, i, i, i, i, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp,
+                                          i, vp, vp, vp, vp, vp, vp, d, d]
+    lib.o2d_points_on_panels_sharded.argtypes = [vp, i, i, vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp]
     lib.external_vel_solver_f_.restype = C.c_float
     lib.external_vel_solver_f_.argtypes = [C.POINTER(i), vp, vp, vp, vp, C.POINTER(i), vp, vp, vp, vp]
     lib.external_vel_solver_tr_f_.restype = C.c_float
@@ -248,6 +251,19 @@ class Context:
             self._h, int(method), int(mem), int(np_), int(nnodes), _ptr(nx), _ptr(ny), _ptr(idx), _ptr(snx), _ptr(sny),
             int(n), _ptr(tx), _ptr(ty), float(cutoff_mult), float(ips), C.byref(moved) if want_count else None))
         return moved.value
+
+    def find_vels_sharded(self, core, results, mem, nv_local, nv_block, vx, vy, vs, vr, np_, nnodes, nx, ny, idx,
+                          pvs, pss, nt, tx, ty, tr, tu, tv, tq=None, fs=(0.0, 0.0)):
+        core = CORE_ID[core] if isinstance(core, str) else int(core)
+        self._check(self.lib.o2d_find_vels_sharded(
+            self._h, core, int(results), int(mem), int(nv_local), int(nv_block), _ptr(vx), _ptr(vy), _ptr(vs), _ptr(vr),
+            int(np_), int(nnodes), _ptr(nx), _ptr(ny), _ptr(idx), _ptr(pvs), _ptr(pss),
+            int(nt), _ptr(tx), _ptr(ty), _ptr(tr), _ptr(tu), _ptr(tv), _ptr(tq), float(fs[0]), float(fs[1])))
+
+    def points_on_panels_sharded(self, mem, ns_local, sx, sy, ss, np_, nnodes, nx, ny, idx, area, pu, pv):
+        self._check(self.lib.o2d_points_on_panels_sharded(
+            self._h, int(mem), int(ns_local), _ptr(sx), _ptr(sy), _ptr(ss), int(np_), int(nnodes),
+            _ptr(nx), _ptr(ny), _ptr(idx), _ptr(area), _ptr(pu), _ptr(pv)))
 
     # -- comm
     @staticmethod

@@ -34,6 +34,7 @@ struct NcclApi {
   int (*CommInitRank)(ncclComm_t*, int, NcclUid, int) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   bool load() {
     if (handle) return true;
@@ -44,13 +45,16 @@ struct NcclApi {
     CommInitRank = (decltype(CommInitRank))dlsym(handle, "ncclCommInitRank");
     CommDestroy = (decltype(CommDestroy))dlsym(handle, "ncclCommDestroy");
     AllGather = (decltype(AllGather))dlsym(handle, "ncclAllGather");
+    AllReduce = (decltype(AllReduce))dlsym(handle, "ncclAllReduce");
     GetErrorString = (decltype(GetErrorString))dlsym(handle, "ncclGetErrorString");
-    return GetUniqueId && CommInitRank && CommDestroy && AllGather && GetErrorString;
+    return GetUniqueId && CommInitRank && CommDestroy && AllGather && AllReduce && GetErrorString;
   }
 };
 static NcclApi g_nccl;
 static std::mutex g_nccl_mu;
-constexpr int kNcclChar = 0;  // ncclInt8 / ncclChar
+constexpr int kNcclChar = 0;     // ncclInt8 / ncclChar
+constexpr int kNcclDouble = 8;   // ncclFloat64
+constexpr int kNcclSum = 0;      // ncclSum
 
 #define bind_device o2d_bind_device
 #define drain_timing o2d_drain_timing
@@ -426,38 +430,96 @@ extern "C" int o2d_panels_on_points(o2d_context* c, int mem,
   return O2D_OK;
 }
 
-int o2d_points_on_panels_device(o2d_context* c, int ns, const float* sx, const float* sy, const float* ss,
-                                   int np, const float* nx, const float* ny, const uint32_t* idx,
-                                   const float* area, float* pu, float* pv) {
-  if (ns <= 0 || np <= 0) return O2D_OK;
-  const int ntiles = (ns + kTile - 1) / kTile;
+// `allreduce`: the particles are this rank's block of a sharded set -- the per-panel sums are reduced
+// over all ranks (ncclAllReduce of 2*Np float64) before they are folded into pu,pv on every rank.
+static int points_on_panels_impl(o2d_context* c, int ns, const float* sx, const float* sy, const float* ss,
+                                 int np, const float* nx, const float* ny, const uint32_t* idx,
+                                 const float* area, float* pu, float* pv, bool allreduce) {
+  if (np <= 0) return O2D_OK;
+  if (ns <= 0 && !allreduce) return O2D_OK;
+  const int ntiles = (std::max(ns, 0) + kTile - 1) / kTile;
   const int ns_padded = ntiles * kTile;
-  CU(c->packed.reserve((size_t)ns_padded * 16));
-  CU(launch_pack_sources(101, ns, sx, sy, ss, nullptr, c->packed.as<float4>(), ns_padded, c->stream));
-  c->launches++;
-  const int nb = (np + 63) / 64;
-  const int slots = c->sm_count * ptpan_occupancy();
-  const int nchunks = choose_chunks(nb, ntiles, slots, 4096);
   PtPanArgs a;
-  a.packed_src = c->packed.as<float4>();
   a.ntiles = ntiles;
-  a.tiles_per_chunk = (ntiles + nchunks - 1) / nchunks;
   a.nx = nx; a.ny = ny; a.idx = idx; a.area = area; a.np = np; a.pu = pu; a.pv = pv;
   a.partial = nullptr;
-  if (nchunks > 1) {
-    CU(c->partial.reserve((size_t)nchunks * 2 * (size_t)np * sizeof(double)));
+  a.packed_src = nullptr;
+  int nchunks = 1;
+  if (ntiles > 0) {
+    CU(c->packed.reserve((size_t)ns_padded * 16));
+    CU(launch_pack_sources(101, ns, sx, sy, ss, nullptr, c->packed.as<float4>(), ns_padded, c->stream));
+    c->launches++;
+    const int nb = (np + 63) / 64;
+    const int slots = c->sm_count * ptpan_occupancy();
+    nchunks = choose_chunks(nb, ntiles, slots, 4096);
+    a.packed_src = c->packed.as<float4>();
+  }
+  a.tiles_per_chunk = ntiles > 0 ? (ntiles + nchunks - 1) / nchunks : 1;
+  if (nchunks > 1 || allreduce) {
+    // one extra [2][np] slot at the end receives the chunk-reduced (and rank-reduced) sums
+    CU(c->partial.reserve(((size_t)nchunks + 1) * 2 * (size_t)np * sizeof(double)));
     a.partial = c->partial.as<double>();
   }
-  {
+  if (ntiles > 0) {
     PairTimer timer(c);
     CU(launch_points_on_panels(a, nchunks, c->stream));
     c->launches++;
     c->pair_launches++;
   }
-  if (nchunks > 1) {
+  if (allreduce) {
+    double* red = a.partial + (size_t)nchunks * 2 * (size_t)np;
+    CU(launch_ptpan_reduce_chunks(a.partial, ntiles > 0 ? nchunks : 0, np, red, c->stream));
+    c->launches++;
+    if (c->nranks > 1) {
+      int r = g_nccl.AllReduce(red, red, (size_t)2 * np, kNcclDouble, kNcclSum, c->comm, c->stream);
+      if (r != 0) return fail(O2D_ERR_COMM, "ncclAllReduce: %s", g_nccl.GetErrorString(r));
+    }
+    CU(launch_ptpan_combine_geom(red, 1, a, c->stream));
+    c->launches++;
+  } else if (nchunks > 1) {
     CU(launch_ptpan_combine_geom(a.partial, nchunks, a, c->stream));
     c->launches++;
   }
+  return O2D_OK;
+}
+
+int o2d_points_on_panels_device(o2d_context* c, int ns, const float* sx, const float* sy, const float* ss,
+                                int np, const float* nx, const float* ny, const uint32_t* idx,
+                                const float* area, float* pu, float* pv) {
+  return points_on_panels_impl(c, ns, sx, sy, ss, np, nx, ny, idx, area, pu, pv, false);
+}
+
+extern "C" int o2d_points_on_panels_sharded(o2d_context* c, int mem,
+                                            int ns_local, const float* sx, const float* sy, const float* ss,
+                                            int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                                            const float* area, float* pu, float* pv) {
+  if (int rc = check_common(c, mem)) return rc;
+  if (c->nranks > 1 && !c->comm) return fail(O2D_ERR_COMM, "communicator not initialised (o2d_comm_init)");
+  if (ns_local < 0 || np < 0 || nnodes < 0) return fail(O2D_ERR_INVALID, "negative count");
+  if (np == 0) return O2D_OK;
+  if (ns_local > 0 && (!sx || !sy || !ss)) return fail(O2D_ERR_INVALID, "NULL particle array");
+  if (!nx || !ny || !idx || !area || !pu || !pv) return fail(O2D_ERR_INVALID, "NULL array");
+  if (mem == O2D_MEM_DEVICE) return points_on_panels_impl(c, ns_local, sx, sy, ss, np, nx, ny, idx, area, pu, pv, true);
+  for (int k = 0; k < 2 * np; ++k)
+    if (idx[k] >= (uint32_t)nnodes) return fail(O2D_ERR_INVALID, "panel node index %u out of range", idx[k]);
+  CU(c->hsrc.reserve(3 * padded_floats(ns_local) + 256));
+  CU(c->htgt.reserve(2 * padded_floats(nnodes) + padded_floats(np)));
+  CU(c->hidx.reserve((size_t)2 * np * sizeof(uint32_t)));
+  CU(c->hout.reserve(kMaxOut * padded_floats(np)));
+  Stager S(c, &c->hsrc), T(c, &c->htgt), O(c, &c->hout);
+  float *dsx = S.take(ns_local), *dsy = S.take(ns_local), *dss = S.take(ns_local);
+  float *dnx = T.take(nnodes), *dny = T.take(nnodes), *darea = T.take(np);
+  float *dpu = O.take(np), *dpv = O.take(np);
+  int rc;
+  if ((rc = h2d(c, dsx, sx, ns_local)) || (rc = h2d(c, dsy, sy, ns_local)) || (rc = h2d(c, dss, ss, ns_local)) ||
+      (rc = h2d(c, dnx, nx, nnodes)) || (rc = h2d(c, dny, ny, nnodes)) || (rc = h2d(c, darea, area, np)) ||
+      (rc = h2d(c, dpu, pu, np)) || (rc = h2d(c, dpv, pv, np)))
+    return rc;
+  CU(cudaMemcpyAsync(c->hidx.p, idx, (size_t)2 * np * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  if ((rc = points_on_panels_impl(c, ns_local, dsx, dsy, dss, np, dnx, dny, c->hidx.as<uint32_t>(), darea, dpu, dpv, true)))
+    return rc;
+  if ((rc = d2h(c, pu, dpu, np)) || (rc = d2h(c, pv, dpv, np))) return rc;
+  CU(cudaStreamSynchronize(c->stream));
   return O2D_OK;
 }
 
@@ -722,7 +784,7 @@ extern "C" int o2d_comm_destroy(o2d_context* c) {
   return O2D_OK;
 }
 
-static int pp_sharded_device(o2d_context* c, int core, int res, int ns_local, int ns_block,
+int o2d_pp_sharded_device(o2d_context* c, int core, int res, int ns_local, int ns_block,
                              const float* sx, const float* sy, const float* ss, const float* sr,
                              int nt, const float* tx, const float* ty, const float* tr, const OutPtrs& out) {
   const int P = c->nranks;
@@ -800,7 +862,7 @@ extern "C" int o2d_points_on_points_sharded(o2d_context* c, int core, int result
   OutPtrs o{};
   if (mem == O2D_MEM_DEVICE) {
     for (int k = 0; k < nout; ++k) o.p[k] = outs[k];
-    return pp_sharded_device(c, core, res, ns_local, ns_block, sx, sy, ss, sr, nt, tx, ty, tr, o);
+    return o2d_pp_sharded_device(c, core, res, ns_local, ns_block, sx, sy, ss, sr, nt, tx, ty, tr, o);
   }
   CU(c->hsrc.reserve(4 * padded_floats(ns_local) + 256));
   CU(c->htgt.reserve(3 * padded_floats(nt) + 256));
@@ -817,7 +879,7 @@ extern "C" int o2d_points_on_points_sharded(o2d_context* c, int core, int result
     o.p[k] = O.take(nt);
     if ((rc = h2d(c, o.p[k], outs[k], nt))) return rc;
   }
-  if ((rc = pp_sharded_device(c, core, res, ns_local, ns_block, dsx, dsy, dss, dsr, nt, dtx, dty, dtr, o))) return rc;
+  if ((rc = o2d_pp_sharded_device(c, core, res, ns_local, ns_block, dsx, dsy, dss, dsr, nt, dtx, dty, dtr, o))) return rc;
   for (int k = 0; k < nout; ++k)
     if ((rc = d2h(c, outs[k], o.p[k], nt))) return rc;
   CU(cudaStreamSynchronize(c->stream));

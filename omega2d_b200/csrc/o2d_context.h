@@ -95,6 +95,9 @@ int o2d_res_from_results(int results);
 int o2d_pp_device(o2d_context* c, int core, int res,
                   int ns, const float* sx, const float* sy, const float* ss, const float* sr,
                   int nt, const float* tx, const float* ty, const float* tr, const o2d::OutPtrs& out);
+int o2d_pp_sharded_device(o2d_context* c, int core, int res, int ns_local, int ns_block,
+                          const float* sx, const float* sy, const float* ss, const float* sr,
+                          int nt, const float* tx, const float* ty, const float* tr, const o2d::OutPtrs& out);
 int o2d_panels_on_points_device(o2d_context* c, int np, const float* nx, const float* ny, const uint32_t* idx,
                                 const float* vs, const float* ss, int nt, const float* tx, const float* ty,
                                 float* tu, float* tv);

@@ -89,6 +89,8 @@ struct PtPanArgs {
 };
 cudaError_t launch_points_on_panels(const PtPanArgs& a, int nchunks, cudaStream_t st);
 cudaError_t launch_ptpan_combine_geom(const double* partial, int nchunks, const PtPanArgs& a, cudaStream_t st);
+// out[2][np] = sum over chunks of partial[chunk][2][np] (zeros when nchunks == 0)
+cudaError_t launch_ptpan_reduce_chunks(const double* partial, int nchunks, int np, double* out, cudaStream_t st);
 int panels_occupancy();
 int ptpan_occupancy();
 

@@ -212,6 +212,18 @@ cudaError_t launch_ptpan_combine_geom(const double* partial, int nchunks, const 
   ptpan_combine_kernel<<<(a.np + 255) / 256, 256, 0, st>>>(partial, nchunks, a.np, a.nx, a.ny, a.idx, a.area, a.pu, a.pv);
   return cudaGetLastError();
 }
+__global__ void __launch_bounds__(256)
+ptpan_reduce_chunks_kernel(const double* __restrict__ partial, int nchunks, int np, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * np) return;
+  double acc = 0.0;
+  for (int c = 0; c < nchunks; ++c) acc += partial[(size_t)c * 2 * (size_t)np + i];
+  out[i] = acc;
+}
+cudaError_t launch_ptpan_reduce_chunks(const double* partial, int nchunks, int np, double* out, cudaStream_t st) {
+  ptpan_reduce_chunks_kernel<<<(2 * np + 255) / 256, 256, 0, st>>>(partial, nchunks, np, out);
+  return cudaGetLastError();
+}
 int ptpan_occupancy() {
   int nb = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, points_on_panels_kernel, kPtPanThreads, 0) != cudaSuccess) return 1;

@@ -63,17 +63,25 @@ struct Panels {
 
 // Convection::find_vels for one particle collection + one surface collection on one target
 // collection, all in device memory: zero -> particles -> panels -> finalize.
+// nv_block > 0: the particles are this rank's block of a sharded set (o2d_points_on_points_sharded).
 int find_vels_device(o2d_context* c, int core, int res, int nv, const float* vx, const float* vy, const float* vs,
                      const float* vr, const Panels& pan, int nt, const float* tx, const float* ty, const float* tr,
-                     float* tu, float* tv, float* tq, double fsx, double fsy) {
-  if (nt <= 0) return O2D_OK;
+                     float* tu, float* tv, float* tq, double fsx, double fsy, int nv_block = 0) {
+  if (nt <= 0 && nv_block <= 0) return O2D_OK;
   float* w = res == RES_UW ? tq : nullptr;
   float* e = res == RES_UE ? tq : nullptr;
-  CU(launch_zero(nt, tu, tv, w, e, c->stream));
-  c->launches++;
+  if (nt > 0) {
+    CU(launch_zero(nt, tu, tv, w, e, c->stream));
+    c->launches++;
+  }
   OutPtrs o{};
   o.p[0] = tu; o.p[1] = tv; o.p[2] = tq;
-  if (int rc = o2d_pp_device(c, core, res, nv, vx, vy, vs, vr, nt, tx, ty, tr, o)) return rc;
+  if (nv_block > 0) {
+    if (int rc = o2d_pp_sharded_device(c, core, res, nv, nv_block, vx, vy, vs, vr, nt, tx, ty, tr, o)) return rc;
+  } else {
+    if (int rc = o2d_pp_device(c, core, res, nv, vx, vy, vs, vr, nt, tx, ty, tr, o)) return rc;
+  }
+  if (nt <= 0) return O2D_OK;
   if (pan.np > 0)
     if (int rc = o2d_panels_on_points_device(c, pan.np, pan.nx, pan.ny, pan.idx, pan.vs, pan.ss, nt, tx, ty, tu, tv))
       return rc;
@@ -149,6 +157,53 @@ extern "C" int o2d_find_vels(o2d_context* c, int core, int results, int mem,
   if (tr && (rc = o2d_h2d(c, dtr, tr, nt))) return rc;
   if ((rc = stage_panels(c, np, nnodes, nx, ny, idx, pvs, pss, &pan))) return rc;
   if ((rc = find_vels_device(c, core, res, nv, dvx, dvy, dvs, dvr, pan, nt, dtx, dty, dtr, dtu, dtv, dtq, fsx, fsy)))
+    return rc;
+  if ((rc = o2d_d2h(c, tu, dtu, nt)) || (rc = o2d_d2h(c, tv, dtv, nt))) return rc;
+  if (res != RES_U && (rc = o2d_d2h(c, tq, dtq, nt))) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  return O2D_OK;
+}
+
+extern "C" int o2d_find_vels_sharded(o2d_context* c, int core, int results, int mem,
+                                     int nv_local, int nv_block,
+                                     const float* vx, const float* vy, const float* vs, const float* vr,
+                                     int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                                     const float* pvs, const float* pss,
+                                     int nt, const float* tx, const float* ty, const float* tr,
+                                     float* tu, float* tv, float* tq, double fsx, double fsy) {
+  if (int rc = o2d_check_common(c, mem)) return rc;
+  if (c->nranks > 1 && !c->comm) return fail(O2D_ERR_COMM, "communicator not initialised (o2d_comm_init)");
+  if (core < 0 || core > 4) return fail(O2D_ERR_INVALID, "unknown core %d", core);
+  if (results == O2D_PSIONLY || results == O2D_VELANDGRAD)
+    return fail(O2D_ERR_UNSUPPORTED, "find_vels computes vel, vel+vort or vel+shear (reference src/Convection.h:172-223)");
+  const int res = o2d_res_from_results(results);
+  if (res < 0) return fail(O2D_ERR_INVALID, "unknown results type %d", results);
+  if (nv_local < 0 || nt < 0 || nv_block <= 0 || nv_local > nv_block)
+    return fail(O2D_ERR_INVALID, "bad counts nv_local=%d nv_block=%d nt=%d", nv_local, nv_block, nt);
+  if (int rc = check_panels(np, nnodes, nx, ny, idx, pvs)) return rc;
+  if (nv_local > 0 && (!vx || !vy || !vs || !vr)) return fail(O2D_ERR_INVALID, "NULL particle array");
+  if (nt > 0 && (!tx || !ty || !tu || !tv)) return fail(O2D_ERR_INVALID, "NULL target array");
+  if (nt > 0 && res != RES_U && !tq) return fail(O2D_ERR_INVALID, "tq must not be NULL for vorticity/shear results");
+  Panels pan;
+  if (mem == O2D_MEM_DEVICE) {
+    pan.np = np; pan.nx = nx; pan.ny = ny; pan.idx = idx; pan.vs = pvs; pan.ss = pss;
+    return find_vels_device(c, core, res, nv_local, vx, vy, vs, vr, pan, nt, tx, ty, tr, tu, tv, tq, fsx, fsy, nv_block);
+  }
+  CU(c->hsrc.reserve(4 * padded_floats(nv_local) + 256));
+  CU(c->htgt.reserve(3 * padded_floats(nt) + 256));
+  CU(c->hout.reserve(kMaxOut * padded_floats(nt) + 256));
+  Stager S(c, &c->hsrc), T(c, &c->htgt), O(c, &c->hout);
+  float *dvx = S.take(nv_local), *dvy = S.take(nv_local), *dvs = S.take(nv_local), *dvr = S.take(nv_local);
+  float *dtx = T.take(nt), *dty = T.take(nt), *dtr = tr ? T.take(nt) : nullptr;
+  float *dtu = O.take(nt), *dtv = O.take(nt), *dtq = tq ? O.take(nt) : nullptr;
+  int rc;
+  if ((rc = o2d_h2d(c, dvx, vx, nv_local)) || (rc = o2d_h2d(c, dvy, vy, nv_local)) || (rc = o2d_h2d(c, dvs, vs, nv_local)) ||
+      (rc = o2d_h2d(c, dvr, vr, nv_local)) || (rc = o2d_h2d(c, dtx, tx, nt)) || (rc = o2d_h2d(c, dty, ty, nt)))
+    return rc;
+  if (tr && (rc = o2d_h2d(c, dtr, tr, nt))) return rc;
+  if ((rc = stage_panels(c, np, nnodes, nx, ny, idx, pvs, pss, &pan))) return rc;
+  if ((rc = find_vels_device(c, core, res, nv_local, dvx, dvy, dvs, dvr, pan, nt, dtx, dty, dtr, dtu, dtv, dtq, fsx, fsy,
+                             nv_block)))
     return rc;
   if ((rc = o2d_d2h(c, tu, dtu, nt)) || (rc = o2d_d2h(c, tv, dtv, nt))) return rc;
   if (res != RES_U && (rc = o2d_d2h(c, tq, dtq, nt))) return rc;

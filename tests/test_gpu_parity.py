@@ -313,3 +313,25 @@ def test_find_vels_and_advect_argument_errors(ctx):
                       4, a, a, a, a.copy(), a.copy())
     assert ei.value.code == o2d.ERR_UNSUPPORTED
     ctx.advect("v2", 2, o2d.MEM_HOST, 0, None, None, None, None, None, None, dt=0.1)   # empty set: no-op
+
+
+def test_sharded_single_rank_find_vels_and_panels(ctx, gs, port):
+    """The sharded entry points with one rank (no communicator) must reproduce the plain calls."""
+    g = gs
+    fs = tuple(g["fs"])
+    vort = (g["x"], g["y"], g["s"], g["r2"])
+    pan = (g["nx"], g["ny"], g["idx"], g["pvs"], g["pss"])
+    plain = ctx.find_vels_np("v2", o2d.VELANDVORT, vort, pan, g["tx"], g["ty"], g["tr"], fs)
+    nt = g["tx"].size
+    out = [np.empty(nt, np.float32) for _ in range(3)]
+    ctx.find_vels_sharded("v2", o2d.VELANDVORT, o2d.MEM_HOST, g["x"].size, g["x"].size, *vort,
+                          g["pvs"].size, g["nx"].size, g["nx"], g["ny"], g["idx"], g["pvs"], g["pss"],
+                          nt, g["tx"], g["ty"], g["tr"], out[0], out[1], out[2], fs)
+    for a, b in zip(out, plain):
+        assert W.rel_err(a, b) < 1e-7
+    area = port.panel_areas(g["nx"], g["ny"], g["idx"])
+    want = ctx.points_on_panels_np(g["x"], g["y"], g["s"], g["nx"], g["ny"], g["idx"], area)
+    pu = np.zeros(area.size, np.float32); pv = np.zeros(area.size, np.float32)
+    ctx.points_on_panels_sharded(o2d.MEM_HOST, g["x"].size, g["x"], g["y"], g["s"], area.size, g["nx"].size,
+                                 g["nx"], g["ny"], g["idx"], area, pu, pv)
+    assert W.rel_err((pu, pv), want) < 1e-7
