@@ -232,6 +232,19 @@ int o2d_clear_inner_layer(o2d_context* ctx, int method, int mem,
                           const float* snx, const float* sny,
                           int n, float* tx, float* ty, float cutoff_mult, float ips, long long* num_moved);
 
+/* ---- status reductions ----------------------------------------------------------------------- */
+
+/*
+ * The per-collection sums Simulation::write_status and Points::update_max_str need (reference
+ * src/Simulation.cpp:765-805): total circulation sum s_i (ElementBase::get_total_circ,
+ * src/ElementBase.h:374-394), impulse (-sum s_i y_i, +sum s_i x_i) (Points::get_total_impulse,
+ * src/Points.h:270-285) and max |s_i| (ElementBase::get_max_str, :362-372), in one pass over
+ * device-resident (or host) arrays.  Sums are float64 in a fixed order, returned as float like the
+ * reference's S; any output pointer may be NULL.  Synchronous: it returns four scalars.
+ */
+int o2d_points_status(o2d_context* ctx, int mem, int n, const float* x, const float* y, const float* s,
+                      float* total_circ, float* impulse_x, float* impulse_y, float* max_str);
+
 /* ---- the reference's existing plugin seam ---------------------------------------------- */
 
 /*

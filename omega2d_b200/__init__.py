@@ -85,6 +85,7 @@ def load_library() -> C.CDLL:
     lib.o2d_find_vels_sharded.argtypes = [vp, i, i, i, i, i, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp,
                                           i, vp, vp, vp, vp, vp, vp, d, d]
     lib.o2d_points_on_panels_sharded.argtypes = [vp, i, i, vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp]
+    lib.o2d_points_status.argtypes = [vp, i, i, vp, vp, vp] + [C.POINTER(C.c_float)] * 4
     lib.external_vel_solver_f_.restype = C.c_float
     lib.external_vel_solver_f_.argtypes = [C.POINTER(i), vp, vp, vp, vp, C.POINTER(i), vp, vp, vp, vp]
     lib.external_vel_solver_tr_f_.restype = C.c_float
@@ -264,6 +265,13 @@ class Context:
         self._check(self.lib.o2d_points_on_panels_sharded(
             self._h, int(mem), int(ns_local), _ptr(sx), _ptr(sy), _ptr(ss), int(np_), int(nnodes),
             _ptr(nx), _ptr(ny), _ptr(idx), _ptr(area), _ptr(pu), _ptr(pv)))
+
+    def points_status(self, mem, n, x, y, s):
+        """-> (total_circ, impulse_x, impulse_y, max_str) as Python floats (float32 values)."""
+        out = [C.c_float() for _ in range(4)]
+        self._check(self.lib.o2d_points_status(self._h, int(mem), int(n), _ptr(x), _ptr(y), _ptr(s),
+                                               *[C.byref(o) for o in out]))
+        return tuple(o.value for o in out)
 
     # -- comm
     @staticmethod

@@ -194,7 +194,7 @@ int o2d_res_from_results(int results) {
 static int pp_run_packed(o2d_context* c, int core, int res, const float4* packed,
                          int tile_begin, int tile_end, int skip_begin, int skip_len,
                          const float* tx, const float* ty, const float* tr, int nt, const OutPtrs& out,
-                         int* chunk_cursor, int nchunks, double* partial_base) {
+                         int* chunk_cursor, int nchunks, double* partial_base, bool fine = false) {
   const int ntiles = tile_end - tile_begin;
   if (ntiles <= 0 || nt <= 0 || nchunks <= 0) return O2D_OK;
   if (nchunks > 1 && partial_base == nullptr) return fail(O2D_ERR_INVALID, "internal: chunked launch without partials");
@@ -209,7 +209,7 @@ static int pp_run_packed(o2d_context* c, int core, int res, const float4* packed
   a.partial = partial_base;
   a.chunk_offset = chunk_cursor ? *chunk_cursor : 0;
   a.tiles_per_chunk = (ntiles + nchunks - 1) / nchunks;
-  CU(launch_pp(core, res, a, nchunks, c->stream));
+  CU(launch_pp(core, res, a, nchunks, c->stream, fine));
   c->launches++;
   c->pair_launches++;
   if (chunk_cursor) *chunk_cursor += nchunks;
@@ -217,17 +217,28 @@ static int pp_run_packed(o2d_context* c, int core, int res, const float4* packed
 }
 
 int o2d_pp_device(o2d_context* c, int core, int res,
-                     int ns, const float* sx, const float* sy, const float* ss, const float* sr,
-                     int nt, const float* tx, const float* ty, const float* tr, const OutPtrs& out) {
+                  int ns, const float* sx, const float* sy, const float* ss, const float* sr,
+                  int nt, const float* tx, const float* ty, const float* tr, const OutPtrs& out) {
   if (ns <= 0 || nt <= 0) return O2D_OK;
-  const int ntiles = (ns + kTile - 1) / kTile;
-  const int ns_padded = ntiles * kTile;
+  const int ns_padded = ((ns + kTile - 1) / kTile) * kTile;   // the packed array is always padded to whole big tiles
   CU(c->packed.reserve((size_t)ns_padded * 16));
   CU(launch_pack_sources(res == RES_VORT ? 100 : core, ns, sx, sy, ss, sr, c->packed.as<float4>(), ns_padded, c->stream));
   c->launches++;
-  const int R = res_targets_per_thread(res);
-  const int nb = (nt + kThreads * R - 1) / (kThreads * R);
-  const int slots = c->sm_count * pp_occupancy(core, res);
+  // Small and medium problems: with the big configuration (256*R targets x 1024 sources per CTA-tile, ~33 us
+  // of work) a few thousand particles occupy a handful of SMs for one long tile, and up to ~200k particles the
+  // coarse units leave the last wave of CTAs uneven.  The fine configuration (128*R/2 targets x 256 sources)
+  // has the same per-SM rate for the velocity kernels (measured 12.86 vs 12.83 pairs/clk/SM at 1M, RM) and
+  // 32x smaller units: 5k particles 58 -> 17 us, 50k 10.7 -> 12.2 pairs/clk/SM, 200k 12.5 -> 12.7.  Above that
+  // the big one is kept (fewer barriers and LDS per pair; V2 with uniform radii: 12.7 vs 12.4).
+  const int Rb = res_targets_per_thread(res);
+  const long long big_units = (long long)((nt + kThreads * Rb - 1) / (kThreads * Rb)) * ((ns + kTile - 1) / kTile);
+  const bool fine = big_units < 96LL * c->sm_count * pp_occupancy(core, res);
+  const int tile = fine ? kFineTile : kTile;
+  const int threads = fine ? kFineThreads : kThreads;
+  const int R = res_targets_per_thread(res, fine);
+  const int ntiles = (ns + tile - 1) / tile;
+  const int nb = (nt + threads * R - 1) / (threads * R);
+  const int slots = c->sm_count * pp_occupancy(core, res, fine);
   const int nchunks = choose_chunks(nb, ntiles, slots, 256);
   double* partial = nullptr;
   if (nchunks > 1) {
@@ -237,7 +248,7 @@ int o2d_pp_device(o2d_context* c, int core, int res,
   {
     PairTimer timer(c);
     int rc = pp_run_packed(c, core, res, c->packed.as<float4>(), 0, ntiles, INT_MAX, 0, tx, ty, tr, nt, out,
-                           nullptr, nchunks, partial);
+                           nullptr, nchunks, partial, fine);
     if (rc) return rc;
   }
   if (nchunks > 1) {

@@ -13,6 +13,10 @@ enum : int { RES_U = 0, RES_UW = 1, RES_UE = 2, RES_UG = 3, RES_VORT = 4 };
 constexpr int kTile = 1024;     // sources per shared-memory tile (16 KiB per stage)
 constexpr int kThreads = 256;   // threads per CTA of the pair-sum kernels
 constexpr int kMaxOut = 6;
+// "fine" configuration of the same kernel for small problems: a CTA-tile is 128*R x 256 pairs instead of
+// 256*R x 1024, so a few thousand particles still spread over all SMs and no CTA runs longer than a few us
+constexpr int kFineTile = 256;
+constexpr int kFineThreads = 128;
 
 struct OutPtrs {
   float* p[kMaxOut];
@@ -53,16 +57,19 @@ inline int res_ncomp(int res) {
   switch (res) { case 0: return 2; case 1: return 4; case 2: return 3; case 3: return 6; case 4: return 1; }
   return 0;
 }
-inline int res_targets_per_thread(int res) { return (res == 0 || res == 4) ? 4 : 2; }
+inline int res_targets_per_thread(int res, bool fine = false) {
+  const int r = (res == 0 || res == 4) ? 4 : 2;
+  return fine ? r / 2 : r;
+}
 
 // ---- launchers implemented per translation unit ------------------------------------------------
 // pair-sum kernel for (core, res); grid = (target blocks, nchunks)
-cudaError_t launch_pp(int core, int res, const PPArgs& a, int nchunks, cudaStream_t st);
+// fine: tile indices in `a` count kFineTile-source tiles and a CTA holds kFineThreads threads
+cudaError_t launch_pp(int core, int res, const PPArgs& a, int nchunks, cudaStream_t st, bool fine = false);
 cudaError_t launch_pp_combine(int res, const double* partial, int nchunks, int nt, const OutPtrs& out,
                               cudaStream_t st);
 // resident CTAs per SM of the (core,res) kernel; cached
-int pp_occupancy(int core, int res);
-size_t pp_smem_bytes();
+int pp_occupancy(int core, int res, bool fine = false);
 
 // source packing: SoA (x,y,s,r) -> pairwise {-x0,-x1,-y0,-y1}{s0,s1,rho0,rho1}, padded to a whole
 // number of tiles with zero-strength copies of the last particle.  mode: core id, or 100 for

@@ -3,49 +3,49 @@
 
 namespace o2d {
 
-template <int CORE> cudaError_t launch_pp_core(int, const PPArgs&, int, cudaStream_t);
-template <int CORE> int pp_occupancy_core(int);
-extern template cudaError_t launch_pp_core<CORE_RM>(int, const PPArgs&, int, cudaStream_t);
-extern template cudaError_t launch_pp_core<CORE_EXP>(int, const PPArgs&, int, cudaStream_t);
-extern template cudaError_t launch_pp_core<CORE_WL>(int, const PPArgs&, int, cudaStream_t);
-extern template cudaError_t launch_pp_core<CORE_V2>(int, const PPArgs&, int, cudaStream_t);
-extern template cudaError_t launch_pp_core<CORE_V3>(int, const PPArgs&, int, cudaStream_t);
-extern template int pp_occupancy_core<CORE_RM>(int);
-extern template int pp_occupancy_core<CORE_EXP>(int);
-extern template int pp_occupancy_core<CORE_WL>(int);
-extern template int pp_occupancy_core<CORE_V2>(int);
-extern template int pp_occupancy_core<CORE_V3>(int);
+template <int CORE> cudaError_t launch_pp_core(int, const PPArgs&, int, cudaStream_t, bool);
+template <int CORE> int pp_occupancy_core(int, bool);
+extern template cudaError_t launch_pp_core<CORE_RM>(int, const PPArgs&, int, cudaStream_t, bool);
+extern template cudaError_t launch_pp_core<CORE_EXP>(int, const PPArgs&, int, cudaStream_t, bool);
+extern template cudaError_t launch_pp_core<CORE_WL>(int, const PPArgs&, int, cudaStream_t, bool);
+extern template cudaError_t launch_pp_core<CORE_V2>(int, const PPArgs&, int, cudaStream_t, bool);
+extern template cudaError_t launch_pp_core<CORE_V3>(int, const PPArgs&, int, cudaStream_t, bool);
+extern template int pp_occupancy_core<CORE_RM>(int, bool);
+extern template int pp_occupancy_core<CORE_EXP>(int, bool);
+extern template int pp_occupancy_core<CORE_WL>(int, bool);
+extern template int pp_occupancy_core<CORE_V2>(int, bool);
+extern template int pp_occupancy_core<CORE_V3>(int, bool);
 
-size_t pp_smem_bytes() { return 2 * (size_t)kTile * 16 + 64; }
-
-cudaError_t launch_pp(int core, int res, const PPArgs& a, int nchunks, cudaStream_t st) {
-  if (res == RES_VORT) return launch_one<CORE_RM, RES_VORT>(a, nchunks, st);
+cudaError_t launch_pp(int core, int res, const PPArgs& a, int nchunks, cudaStream_t st, bool fine) {
+  if (res == RES_VORT)
+    return fine ? launch_one<CORE_RM, RES_VORT, true>(a, nchunks, st) : launch_one<CORE_RM, RES_VORT, false>(a, nchunks, st);
   switch (core) {
-    case CORE_RM:  return launch_pp_core<CORE_RM>(res, a, nchunks, st);
-    case CORE_EXP: return launch_pp_core<CORE_EXP>(res, a, nchunks, st);
-    case CORE_WL:  return launch_pp_core<CORE_WL>(res, a, nchunks, st);
-    case CORE_V2:  return launch_pp_core<CORE_V2>(res, a, nchunks, st);
-    case CORE_V3:  return launch_pp_core<CORE_V3>(res, a, nchunks, st);
+    case CORE_RM:  return launch_pp_core<CORE_RM>(res, a, nchunks, st, fine);
+    case CORE_EXP: return launch_pp_core<CORE_EXP>(res, a, nchunks, st, fine);
+    case CORE_WL:  return launch_pp_core<CORE_WL>(res, a, nchunks, st, fine);
+    case CORE_V2:  return launch_pp_core<CORE_V2>(res, a, nchunks, st, fine);
+    case CORE_V3:  return launch_pp_core<CORE_V3>(res, a, nchunks, st, fine);
   }
   return cudaErrorInvalidValue;
 }
 
-int pp_occupancy(int core, int res) {
-  static int cache[5][5] = {};
+int pp_occupancy(int core, int res, bool fine) {
+  static int cache[2][5][5] = {};
   if (core < 0 || core > 4 || res < 0 || res > 4) return 1;
-  if (cache[core][res] == 0) {
+  int& slot = cache[fine ? 1 : 0][core][res];
+  if (slot == 0) {
     int v = 1;
-    if (res == RES_VORT) v = occupancy_one<CORE_RM, RES_VORT>();
+    if (res == RES_VORT) v = fine ? occupancy_one<CORE_RM, RES_VORT, true>() : occupancy_one<CORE_RM, RES_VORT, false>();
     else switch (core) {
-      case CORE_RM:  v = pp_occupancy_core<CORE_RM>(res); break;
-      case CORE_EXP: v = pp_occupancy_core<CORE_EXP>(res); break;
-      case CORE_WL:  v = pp_occupancy_core<CORE_WL>(res); break;
-      case CORE_V2:  v = pp_occupancy_core<CORE_V2>(res); break;
-      case CORE_V3:  v = pp_occupancy_core<CORE_V3>(res); break;
+      case CORE_RM:  v = pp_occupancy_core<CORE_RM>(res, fine); break;
+      case CORE_EXP: v = pp_occupancy_core<CORE_EXP>(res, fine); break;
+      case CORE_WL:  v = pp_occupancy_core<CORE_WL>(res, fine); break;
+      case CORE_V2:  v = pp_occupancy_core<CORE_V2>(res, fine); break;
+      case CORE_V3:  v = pp_occupancy_core<CORE_V3>(res, fine); break;
     }
-    cache[core][res] = v;
+    slot = v;
   }
-  return cache[core][res];
+  return slot;
 }
 
 cudaError_t launch_pp_combine(int res, const double* partial, int nchunks, int nt, const OutPtrs& out,

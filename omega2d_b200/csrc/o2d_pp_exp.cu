@@ -1,6 +1,6 @@
 // o2d_pp_exp.cu -- pair-sum kernels for the CORE_EXP core (one TU per core: parallel builds).
 #include "o2d_pp_impl.cuh"
 namespace o2d {
-template cudaError_t launch_pp_core<CORE_EXP>(int, const PPArgs&, int, cudaStream_t);
-template int pp_occupancy_core<CORE_EXP>(int);
+template cudaError_t launch_pp_core<CORE_EXP>(int, const PPArgs&, int, cudaStream_t, bool);
+template int pp_occupancy_core<CORE_EXP>(int, bool);
 }  // namespace o2d

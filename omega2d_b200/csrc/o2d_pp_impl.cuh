@@ -245,53 +245,71 @@ pp_combine_kernel(const double* __restrict__ partial, int nchunks, int nt, const
 // ---- per-core launcher (explicitly instantiated in o2d_pp_<core>.cu) ---------------------------
 namespace o2d {
 
-template <int CORE, int RES>
+template <int CORE, int RES, bool FINE>
+struct PPConfig {
+  static constexpr int THREADS = FINE ? kFineThreads : kThreads;
+  static constexpr int TILE = FINE ? kFineTile : kTile;
+  static constexpr int R = FINE ? ResTraits<RES>::R / 2 : ResTraits<RES>::R;
+  static constexpr size_t SMEM = 2 * (size_t)TILE * 16 + 64;
+  static auto kernel() { return pp_kernel<CORE, RES, THREADS, TILE, R>; }
+};
+
+template <int CORE, int RES, bool FINE>
 static cudaError_t launch_one(const PPArgs& a, int nchunks, cudaStream_t st) {
-  constexpr int R = ResTraits<RES>::R;
-  auto kern = pp_kernel<CORE, RES, kThreads, kTile>;
-  const size_t smem = pp_smem_bytes();
+  using C = PPConfig<CORE, RES, FINE>;
+  auto kern = C::kernel();
   static bool configured = false;   // one context per thread, but the attribute is per function
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const int nb = (a.nt + kThreads * R - 1) / (kThreads * R);
+  const int nb = (a.nt + C::THREADS * C::R - 1) / (C::THREADS * C::R);
   dim3 grid(nb, nchunks, 1);
-  kern<<<grid, kThreads, smem, st>>>(a);
+  kern<<<grid, C::THREADS, C::SMEM, st>>>(a);
   return cudaGetLastError();
 }
 
-template <int CORE, int RES>
+template <int CORE, int RES, bool FINE>
 static int occupancy_one() {
-  auto kern = pp_kernel<CORE, RES, kThreads, kTile>;
-  const size_t smem = pp_smem_bytes();
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  using C = PPConfig<CORE, RES, FINE>;
+  auto kern = C::kernel();
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
   int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem) != cudaSuccess) return 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, C::THREADS, C::SMEM) != cudaSuccess) return 1;
   return nb > 0 ? nb : 1;
 }
 
-template <int CORE>
-cudaError_t launch_pp_core(int res, const PPArgs& a, int nchunks, cudaStream_t st) {
+template <int CORE, bool FINE>
+static cudaError_t launch_pp_core_cfg(int res, const PPArgs& a, int nchunks, cudaStream_t st) {
   switch (res) {
-    case RES_U:  return launch_one<CORE, RES_U>(a, nchunks, st);
-    case RES_UW: return launch_one<CORE, RES_UW>(a, nchunks, st);
-    case RES_UE: return launch_one<CORE, RES_UE>(a, nchunks, st);
-    case RES_UG: return launch_one<CORE, RES_UG>(a, nchunks, st);
+    case RES_U:  return launch_one<CORE, RES_U, FINE>(a, nchunks, st);
+    case RES_UW: return launch_one<CORE, RES_UW, FINE>(a, nchunks, st);
+    case RES_UE: return launch_one<CORE, RES_UE, FINE>(a, nchunks, st);
+    case RES_UG: return launch_one<CORE, RES_UG, FINE>(a, nchunks, st);
   }
   return cudaErrorInvalidValue;
 }
 
 template <int CORE>
-int pp_occupancy_core(int res) {
+cudaError_t launch_pp_core(int res, const PPArgs& a, int nchunks, cudaStream_t st, bool fine) {
+  return fine ? launch_pp_core_cfg<CORE, true>(res, a, nchunks, st) : launch_pp_core_cfg<CORE, false>(res, a, nchunks, st);
+}
+
+template <int CORE, bool FINE>
+static int pp_occupancy_core_cfg(int res) {
   switch (res) {
-    case RES_U:  return occupancy_one<CORE, RES_U>();
-    case RES_UW: return occupancy_one<CORE, RES_UW>();
-    case RES_UE: return occupancy_one<CORE, RES_UE>();
-    case RES_UG: return occupancy_one<CORE, RES_UG>();
+    case RES_U:  return occupancy_one<CORE, RES_U, FINE>();
+    case RES_UW: return occupancy_one<CORE, RES_UW, FINE>();
+    case RES_UE: return occupancy_one<CORE, RES_UE, FINE>();
+    case RES_UG: return occupancy_one<CORE, RES_UG, FINE>();
   }
   return 1;
+}
+
+template <int CORE>
+int pp_occupancy_core(int res, bool fine) {
+  return fine ? pp_occupancy_core_cfg<CORE, true>(res) : pp_occupancy_core_cfg<CORE, false>(res);
 }
 
 }  // namespace o2d

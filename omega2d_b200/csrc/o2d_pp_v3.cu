@@ -1,6 +1,6 @@
 // o2d_pp_v3.cu -- pair-sum kernels for the CORE_V3 core (one TU per core: parallel builds).
 #include "o2d_pp_impl.cuh"
 namespace o2d {
-template cudaError_t launch_pp_core<CORE_V3>(int, const PPArgs&, int, cudaStream_t);
-template int pp_occupancy_core<CORE_V3>(int);
+template cudaError_t launch_pp_core<CORE_V3>(int, const PPArgs&, int, cudaStream_t, bool);
+template int pp_occupancy_core<CORE_V3>(int, bool);
 }  // namespace o2d

@@ -252,6 +252,11 @@ class Port:
                   float(cutoff_factor), float(ips), int(max_iter))
         assert moved >= 0
         return x, y, int(moved)
+    def points_status(self, x, y, s):
+        x, y, s = map(_f32, (x, y, s))
+        out = [C.c_float() for _ in range(4)]
+        self.lib.o2d_oracle_points_status(int(x.size), _f(x), _f(y), _f(s), *[C.byref(o) for o in out])
+        return tuple(o.value for o in out)
 
 class Ref:
     """The unmodified reference templates for ONE core (oracle/_ref/libo2dref_<core>.so)."""

@@ -233,13 +233,14 @@ def test_device_memory_path_and_determinism(ctx):
 
 def test_sharded_single_rank_equals_plain(ctx):
     """o2d_points_on_points_sharded with one rank (no communicator) takes the chunked
-    local-block path and must equal the plain call bit for bit."""
+    local-block path and must equal the plain call (same pair terms; the sums are grouped by 1024-source tiles in
+    the sharded path and by 256-source tiles in the plain path at this size, so not bit for bit)."""
     sx, sy, ss, sr = W.gaussian_blob(30000, seed=6)
     a = ctx.points_on_points_np("v2", o2d.VELONLY, sx, sy, ss, sr, sx, sy, sr)
     tu = np.zeros(30000, np.float32); tv = np.zeros(30000, np.float32)
     ctx.points_on_points_sharded("v2", o2d.VELONLY, o2d.MEM_HOST, 30000, 30000, sx, sy, ss, sr,
                                  30000, sx, sy, sr, tu, tv)
-    assert W.rel_err((tu, tv), a) < 1e-7
+    assert W.rel_err((tu, tv), a) < 1e-6
 
 
 # ---- device-resident find_vels / convection step (SURVEY 8f rank 1) -----------------------------------
@@ -328,10 +329,32 @@ def test_sharded_single_rank_find_vels_and_panels(ctx, gs, port):
                           g["pvs"].size, g["nx"].size, g["nx"], g["ny"], g["idx"], g["pvs"], g["pss"],
                           nt, g["tx"], g["ty"], g["tr"], out[0], out[1], out[2], fs)
     for a, b in zip(out, plain):
-        assert W.rel_err(a, b) < 1e-7
+        assert W.rel_err(a, b) < 1e-6     # same sums, grouped differently (sharded: big tiles; plain small set: fine tiles)
     area = port.panel_areas(g["nx"], g["ny"], g["idx"])
     want = ctx.points_on_panels_np(g["x"], g["y"], g["s"], g["nx"], g["ny"], g["idx"], area)
     pu = np.zeros(area.size, np.float32); pv = np.zeros(area.size, np.float32)
     ctx.points_on_panels_sharded(o2d.MEM_HOST, g["x"].size, g["x"], g["y"], g["s"], area.size, g["nx"].size,
                                  g["nx"], g["ny"], g["idx"], area, pu, pv)
     assert W.rel_err((pu, pv), want) < 1e-7
+
+
+@pytest.mark.parametrize("n", [0, 1, 1000, 300001])
+def test_points_status_reductions(n, ctx, port):
+    """circulation / impulse / max strength.  The GPU sums in float64; the reference's impulse is a serial float
+    sum whose own rounding error grows with N, so both are compared with the float64 value of the same sums."""
+    import torch
+    x, y, s, _ = W.gaussian_blob(max(n, 1), seed=5, signed=True)
+    x, y, s = x[:n], y[:n], (s[:n] * max(n, 1)).astype(np.float32)
+    got = ctx.points_status(o2d.MEM_HOST, n, x, y, s)
+    want = port.points_status(x, y, s)
+    s64, x64, y64 = s.astype(np.float64), x.astype(np.float64), y.astype(np.float64)
+    exact = (s64.sum(), -(s64 * y64).sum(), (s64 * x64).sum(), np.abs(s64).max() if n else 1.0)
+    scale = max(np.abs(s64).sum(), 1e-30)
+    for k in range(3):
+        assert abs(got[k] - exact[k]) <= 1e-6 * scale
+        assert abs(got[k] - exact[k]) <= abs(want[k] - exact[k]) + 1e-7 * scale      # never worse than the reference
+    assert got[3] == np.float32(exact[3]) == want[3]
+    assert got[0] == want[0] or abs(got[0] - want[0]) <= 1e-7 * scale                 # both are float64 sums
+    if n:
+        d = [torch.from_numpy(a).cuda() for a in (x, y, s)]
+        assert ctx.points_status(o2d.MEM_DEVICE, n, *d) == got                        # device path, bit-reproducible
