@@ -178,6 +178,17 @@ int o2d_advect(o2d_context* ctx, int core, int order, int mem,
                int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
                const float* pvs, const float* pss, double fsx, double fsy, double dt);
 
+/*
+ * Surfaces::add_solved_rot_strengths / add_rot_strengths_base (reference src/Surfaces.h:556-620), which
+ * find_vels applies with factor +1 before and -1 after the sums (src/Convection.h:186-189,219-222):
+ * adds to vs,ss the vortex and source sheet strengths equivalent to the solid-body rotation of the
+ * panels' body at angular rate `rotvel` (= factor * rotation rate) about its geometric centre (cx,cy),
+ * from the body's UNTRANSFORMED node coordinates ux,uy and the panel lengths `area`.
+ */
+int o2d_add_rot_strengths(o2d_context* ctx, int mem, int np, int nnodes, const float* ux, const float* uy,
+                          const uint32_t* idx, const float* area, float cx, float cy, float rotvel,
+                          float* vs, float* ss);
+
 /* ---- BEM influence coefficients ------------------------------------------------------------ */
 
 /*

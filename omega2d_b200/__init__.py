@@ -86,6 +86,7 @@ def load_library() -> C.CDLL:
                                           i, vp, vp, vp, vp, vp, vp, d, d]
     lib.o2d_points_on_panels_sharded.argtypes = [vp, i, i, vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp]
     lib.o2d_points_status.argtypes = [vp, i, i, vp, vp, vp] + [C.POINTER(C.c_float)] * 4
+    lib.o2d_add_rot_strengths.argtypes = [vp, i, i, i, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, vp, vp]
     lib.external_vel_solver_f_.restype = C.c_float
     lib.external_vel_solver_f_.argtypes = [C.POINTER(i), vp, vp, vp, vp, C.POINTER(i), vp, vp, vp, vp]
     lib.external_vel_solver_tr_f_.restype = C.c_float
@@ -272,6 +273,11 @@ class Context:
         self._check(self.lib.o2d_points_status(self._h, int(mem), int(n), _ptr(x), _ptr(y), _ptr(s),
                                                *[C.byref(o) for o in out]))
         return tuple(o.value for o in out)
+
+    def add_rot_strengths(self, mem, np_, nnodes, ux, uy, idx, area, center, rotvel, vs, ss):
+        self._check(self.lib.o2d_add_rot_strengths(self._h, int(mem), int(np_), int(nnodes), _ptr(ux), _ptr(uy), _ptr(idx),
+                                                   _ptr(area), float(center[0]), float(center[1]), float(rotvel),
+                                                   _ptr(vs), _ptr(ss)))
 
     # -- comm
     @staticmethod

@@ -52,6 +52,33 @@ move23_kernel(int n, float* x, float* y, float* u1, float* v1, const float* __re
   y[i] = y[i] + dt * fv;
 }
 
+// Surfaces::add_rot_strengths_base (reference src/Surfaces.h:571-620): sheet strengths that stand for the
+// solid-body rotation of the body the panels belong to, ADDED to vs/ss.  Same float expression order.
+__host__ __device__ inline void rot_strength_one(int i, const float* ux, const float* uy, const uint32_t* idx,
+                                                 const float* area, float cx, float cy, float rotvel,
+                                                 float* vs, float* ss) {
+  const uint32_t j = idx[2 * i], jp1 = idx[2 * i + 1];
+  const float dx = 0.5f * (ux[j] + ux[jp1]) - cx;
+  const float dy = 0.5f * (uy[j] + uy[jp1]) - cy;
+  const float ui = -rotvel * dy;
+  const float vi = rotvel * dx;
+  float panelx = ux[jp1] - ux[j];
+  float panely = uy[jp1] - uy[j];
+  const float oopanell = 1.0f / area[i];
+  panelx *= oopanell;
+  panely *= oopanell;
+  vs[i] += -1.0f * (ui * panelx + vi * panely);
+  ss[i] += -1.0f * (ui * panely - vi * panelx);
+}
+
+__global__ void __launch_bounds__(256)
+rot_strengths_kernel(int np, const float* __restrict__ ux, const float* __restrict__ uy,
+                     const uint32_t* __restrict__ idx, const float* __restrict__ area, float cx, float cy,
+                     float rotvel, float* vs, float* ss) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < np) rot_strength_one(i, ux, uy, idx, area, cx, cy, rotvel, vs, ss);
+}
+
 struct Panels {
   int np = 0;
   const float* nx = nullptr;
@@ -116,6 +143,26 @@ int check_panels(int np, int nnodes, const float* nx, const float* ny, const uin
 }
 
 }  // namespace
+
+extern "C" int o2d_add_rot_strengths(o2d_context* c, int mem, int np, int nnodes, const float* ux, const float* uy,
+                                     const uint32_t* idx, const float* area, float cx, float cy, float rotvel,
+                                     float* vs, float* ss) {
+  if (int rc = o2d_check_common(c, mem)) return rc;
+  if (np < 0 || nnodes < 0) return fail(O2D_ERR_INVALID, "negative count");
+  if (np == 0) return O2D_OK;
+  if (!ux || !uy || !idx || !area || !vs || !ss) return fail(O2D_ERR_INVALID, "NULL array");
+  if (mem == O2D_MEM_HOST) {
+    // O(Np) on arrays that live on the host: the reference's own loop, nothing worth a round trip
+    for (int k = 0; k < 2 * np; ++k)
+      if (idx[k] >= (uint32_t)nnodes) return fail(O2D_ERR_INVALID, "panel node index %u out of range", idx[k]);
+    for (int i = 0; i < np; ++i) rot_strength_one(i, ux, uy, idx, area, cx, cy, rotvel, vs, ss);
+    return O2D_OK;
+  }
+  rot_strengths_kernel<<<(np + 255) / 256, 256, 0, c->stream>>>(np, ux, uy, idx, area, cx, cy, rotvel, vs, ss);
+  CU(cudaGetLastError());
+  c->launches++;
+  return O2D_OK;
+}
 
 extern "C" int o2d_find_vels(o2d_context* c, int core, int results, int mem,
                              int nv, const float* vx, const float* vy, const float* vs, const float* vr,

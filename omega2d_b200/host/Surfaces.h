@@ -57,6 +57,29 @@ public:
   bool is_augmented() const { return false; }          // no attached Body in this layer (src/Surfaces.h:304-313)
   S get_vol() const { return S(0); }
 
+  // Solid-body rotation of the parent body.  The reference reads the rate from its Body object and the centre
+  // from set_geom_center (src/Surfaces.h:540-566,623-676); this layer has no Body class, so both are given.
+  void set_body_rotation(const S _cx, const S _cy, const S _rotvel) { rot_c[0] = _cx; rot_c[1] = _cy; rot_vel = _rotvel; }
+  // reference src/Surfaces.h:556-620: add factor * (sheet strengths equivalent to the body's rotation)
+  void add_solved_rot_strengths(const S _factor) {
+    if (rot_vel == S(0) || !ps[0] || !ps[1]) return;
+    const S rotvel = _factor * rot_vel;
+    for (size_t i = 0; i < np; i++) {
+      const size_t j = idx[2*i], jp1 = idx[2*i+1];
+      const S dx = 0.5 * (this->x[0][j] + this->x[0][jp1]) - rot_c[0];
+      const S dy = 0.5 * (this->x[1][j] + this->x[1][jp1]) - rot_c[1];
+      const S ui = -rotvel * dy;
+      const S vi =  rotvel * dx;
+      S panelx = this->x[0][jp1] - this->x[0][j];
+      S panely = this->x[1][jp1] - this->x[1][j];
+      const S oopanell = 1.0 / area[i];
+      panelx *= oopanell;
+      panely *= oopanell;
+      (*ps[0])[i] += -1.0 * (ui*panelx + vi*panely);
+      (*ps[1])[i] += -1.0 * (ui*panely - vi*panelx);
+    }
+  }
+
   // panel length, unit tangent and normal (reference src/Surfaces.h:682-726); the normal points into
   // the fluid, to the left when walking from node 0 to node 1
   void compute_bases() {
@@ -107,5 +130,7 @@ protected:
   Vector<S> nbc;                                               // normal-velocity boundary condition per panel
   std::array<Vector<S>,Dimensions> pu;
   std::array<std::optional<Vector<S>>,2> ps;
+  S rot_c[2] = {S(0), S(0)};
+  S rot_vel = S(0);
 };
 #endif

@@ -257,6 +257,13 @@ class Port:
         out = [C.c_float() for _ in range(4)]
         self.lib.o2d_oracle_points_status(int(x.size), _f(x), _f(y), _f(s), *[C.byref(o) for o in out])
         return tuple(o.value for o in out)
+    def add_rot_strengths(self, ux, uy, idx, area, center, rotvel, vs, ss):
+        ux, uy, area = map(_f32, (ux, uy, area)); idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        vs, ss = np.array(vs, np.float32), np.array(ss, np.float32)
+        f = self.lib.o2d_oracle_add_rot_strengths
+        f.argtypes = [C.c_int, _fp, _fp, _up, _fp, C.c_float, C.c_float, C.c_float, _fp, _fp]
+        f(int(vs.size), _f(ux), _f(uy), _u(idx), _f(area), float(center[0]), float(center[1]), float(rotvel), _f(vs), _f(ss))
+        return vs, ss
 
 class Ref:
     """The unmodified reference templates for ONE core (oracle/_ref/libo2dref_<core>.so)."""
@@ -421,6 +428,16 @@ class Ref:
                float(cutoff_factor), float(ips))
         assert rc == 0
         return (x, y) if s is None else (x, y, s)
+    def add_rot_strengths(self, nx, ny, idx, rotvel, vs, ss):
+        """-> (vs, ss, (cx, cy)) from the reference's own body-bound Surfaces."""
+        nx, ny = map(_f32, (nx, ny)); idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        vs, ss = np.array(vs, np.float32), np.array(ss, np.float32)
+        cx, cy = C.c_float(), C.c_float()
+        f = self.lib.o2dref_add_rot_strengths
+        f.argtypes = [C.c_int, C.c_int, _fp, _fp, _up, C.c_float, _fp, _fp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        rc = f(int(vs.size), int(nx.size), _f(nx), _f(ny), _u(idx), float(rotvel), _f(vs), _f(ss), C.byref(cx), C.byref(cy))
+        assert rc == 0
+        return vs, ss, (cx.value, cy.value)
 
 def host_cores() -> int:
     """Cores this process may run on (what OpenMP would use by default)."""

@@ -464,4 +464,28 @@ int o2dref_clear_inner_layer(int method, int np, int nnodes, const float* nx, co
   return 0;
 }
 
+
+// reference Surfaces::add_rot_strengths_base (src/Surfaces.h:571-620) on a body-bound Surfaces attached to a
+// Body (so that the untransformed coordinates and the geometric centre exist, :623-676).  Returns the
+// geometric centre the reference derived in (cx, cy) and the updated strengths in vs, ss.
+int o2dref_add_rot_strengths(int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                             float rotvel, float* vs, float* ss, float* cx, float* cy) {
+  StdoutMute mute;
+  std::vector<float> px(2 * (size_t)nnodes);
+  for (int i = 0; i < nnodes; ++i) { px[2*i] = nx[i]; px[2*i+1] = ny[i]; }
+  std::vector<Int> pidx(idx, idx + 2 * (size_t)np);
+  std::vector<float> val(2 * (size_t)np);
+  for (int i = 0; i < np; ++i) { val[2*i] = vs[i]; val[2*i+1] = ss[i]; }
+  auto body = std::make_shared<Body>();
+  Surfaces<float> s(ElementPacket<float>(px, pidx, val, (size_t)np, 1), active, bodybound, body);
+  s.transform(0.0);                 // body at rest at the origin: x = ux, tc = utc (src/Surfaces.h:729-752)
+  s.add_rot_strengths_base(rotvel);
+  const auto& a = s.get_str();
+  const auto& b = s.get_src_str();
+  for (int i = 0; i < np; ++i) { vs[i] = a[i]; ss[i] = b[i]; }
+  const auto tc = s.get_geom_center();
+  *cx = tc[0]; *cy = tc[1];
+  return 0;
+}
+
 }  // extern "C"

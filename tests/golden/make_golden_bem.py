@@ -44,6 +44,10 @@ def main():
     pu = rng.normal(size=143).astype(np.float32); pv = rng.normal(size=143).astype(np.float32)
     nbc = (0.1 * rng.normal(size=143)).astype(np.float32)
     out.update(pu=pu, pv=pv, nbc=nbc, rhs_a=R.vels_to_rhs_panels(ax, ay, aidx, pu, pv, nbc))
+    # Surfaces::add_rot_strengths_base on a body-bound copy of C (off-centre body, unequal panels), rate 0.7
+    vs0 = rng.normal(size=97).astype(np.float32); ss0 = rng.normal(size=97).astype(np.float32)
+    rvs, rss, ctr = R.add_rot_strengths(cx, cy, cidx, 0.7, vs0, ss0)
+    out.update(rot_vs0=vs0, rot_ss0=ss0, rot_vs=rvs, rot_ss=rss, rot_center=np.array(ctr, np.float32), rot_rate=np.float32(0.7))
     path = os.path.join(ROOT, "tests", "golden", "ref_golden_bem.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")

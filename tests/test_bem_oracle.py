@@ -77,3 +77,16 @@ def test_uniform_flow_is_solved_by_the_matrix(gb, port):
     th = np.arctan2(0.5 * (ay[i0] + ay[i1]), 0.5 * (ax[i0] + ax[i1]))
     # surface speed of potential flow past a circle is 2 U |sin(theta)|; the sheet strength equals it in magnitude
     assert np.abs(np.abs(gam) - np.abs(2.0 * np.sin(th))).max() < 2e-2
+
+
+def test_rot_strengths_golden(gb, port):
+    """Surfaces::add_rot_strengths_base: the reference's own body-bound Surfaces (geometric centre included)."""
+    cx, cy, cidx = surf(gb, "c")
+    area = gb["bases_c"][4]
+    vs, ss = port.add_rot_strengths(cx, cy, cidx, area, tuple(gb["rot_center"]), float(gb["rot_rate"]), gb["rot_vs0"], gb["rot_ss0"])
+    np.testing.assert_allclose(vs, gb["rot_vs"], atol=3e-7)
+    np.testing.assert_allclose(ss, gb["rot_ss"], atol=3e-7)
+    # adding with the opposite factor restores the strengths (find_vels: +1 before, -1 after the sums)
+    vs2, ss2 = port.add_rot_strengths(cx, cy, cidx, area, tuple(gb["rot_center"]), -float(gb["rot_rate"]), vs, ss)
+    np.testing.assert_allclose(vs2, gb["rot_vs0"], atol=3e-7)
+    np.testing.assert_allclose(ss2, gb["rot_ss0"], atol=3e-7)

@@ -77,3 +77,21 @@ def test_coeff_device_memory_path(gb, ctx):
     with pytest.raises(o2d.O2DError):   # odd leading dimension is rejected for device memory
         ctx.panels_on_panels_coeff(o2d.MEM_DEVICE, 143, 143, d[0], d[1], didx, d[2], 143, 143, d[0], d[1], didx, d[2],
                                    d[3], d[4], d[5], d[6], 1, 1, 287, c)
+
+
+def test_rot_strengths(gb, ctx):
+    import torch
+    cx, cy, cidx = surf(gb, "c")
+    area = np.ascontiguousarray(gb["bases_c"][4])
+    ctr, rate = tuple(gb["rot_center"]), float(gb["rot_rate"])
+    vs, ss = gb["rot_vs0"].copy(), gb["rot_ss0"].copy()
+    ctx.add_rot_strengths(o2d.MEM_HOST, 97, 97, cx, cy, cidx, area, ctr, rate, vs, ss)
+    np.testing.assert_allclose(vs, gb["rot_vs"], atol=3e-7)
+    np.testing.assert_allclose(ss, gb["rot_ss"], atol=3e-7)
+    dev = torch.device("cuda:0")
+    d = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (cx, cy, area, gb["rot_vs0"], gb["rot_ss0"])]
+    didx = torch.from_numpy(cidx.astype(np.int32)).to(dev)
+    ctx.add_rot_strengths(o2d.MEM_DEVICE, 97, 97, d[0], d[1], didx, d[2], ctr, rate, d[3], d[4])
+    ctx.synchronize()
+    np.testing.assert_allclose(d[3].cpu().numpy(), gb["rot_vs"], atol=3e-7)
+    np.testing.assert_allclose(d[4].cpu().numpy(), gb["rot_ss"], atol=3e-7)

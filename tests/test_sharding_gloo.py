@@ -76,3 +76,44 @@ def test_two_rank_gather_equals_single_process(n):
         assert p.exitcode == 0
     # padding adds exact zeros, so the sums agree to double-accumulation order (bitwise in practice)
     assert ret.get(timeout=5) < 1e-7
+
+
+def _panel_worker(rank, world, port_no, n, ret):
+    """BEM right-hand side with sharded particles: per-rank reciprocity sums, all-reduce, same result everywhere
+    (the host-side logic of o2d_points_on_panels_sharded)."""
+    import oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    x, y, s, _ = W.annulus_blobs(n, seed=12)
+    nx, ny, idx, _, _ = W.circle_panels(64, radius=0.5)
+    lo, hi = sharding.block_range(n, world, rank)
+    P = oracle.port()
+    area = P.panel_areas(nx, ny, idx)
+    if hi > lo:
+        pu, pv = P.points_on_panels(x[lo:hi], y[lo:hi], s[lo:hi], nx, ny, idx, area)   # from zero: -(local sum)/area
+    else:
+        pu, pv = np.zeros(64, np.float32), np.zeros(64, np.float32)
+    t = torch.from_numpy(np.stack([pu, pv]).astype(np.float64))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    want = P.points_on_panels(x, y, s, nx, ny, idx, area)
+    err = W.rel_err((t[0].numpy(), t[1].numpy()), want)
+    e = torch.tensor([err], dtype=torch.float64)
+    dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ret.put(float(e))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [777, 1])
+def test_two_rank_panel_sums_allreduce(n):
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port_no = _free_port()
+    procs = [ctx.Process(target=_panel_worker, args=(r, 2, port_no, n, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ret.get(timeout=5) < 1e-6
