@@ -380,8 +380,10 @@ int o2d_panels_on_points_device(o2d_context* c, int np, const float* nx, const f
   CU(c->panel_packed.reserve((size_t)np_padded * 32));
   CU(launch_pack_panels(np, nx, ny, idx, vs, ss, c->panel_packed.as<float4>(), np_padded, c->stream));
   c->launches++;
-  const int nb = (nt + 127) / 128;
-  const int slots = c->sm_count * panels_occupancy();
+  // two targets per thread halve the shared-memory reads per pair; one per thread when that would leave SMs idle
+  const int rpt = (nt >= 2 * 256 * c->sm_count * panels_occupancy(2) || (nt >= 256 * c->sm_count && ntiles >= 8)) ? 2 : 1;
+  const int nb = (nt + 128 * rpt - 1) / (128 * rpt);
+  const int slots = c->sm_count * panels_occupancy(rpt);
   const int nchunks = choose_chunks(nb, ntiles, slots, 256);
   PanelArgs a;
   a.packed = c->panel_packed.as<float4>();
@@ -397,7 +399,7 @@ int o2d_panels_on_points_device(o2d_context* c, int np, const float* nx, const f
   }
   {
     PairTimer timer(c);
-    CU(launch_panels_on_points(a, nchunks, c->stream));
+    CU(launch_panels_on_points(a, nchunks, rpt, c->stream));
     c->launches++;
     c->pair_launches++;
   }

@@ -29,7 +29,10 @@ namespace {
 constexpr int kCoefThreads = 128;
 constexpr int kCoefSrcTile = 64;
 
-// per panel: {x0, y0, px, py} {cx, cy, area, 1/len}
+// per panel: {x0, y0, Hx, Hy} {cx, cy, area, thr} {Ux, Uy, -, -}
+//   H = -p/2 and thr = |H|^2/kFarZeta2 feed panel_far2 (o2d_device.cuh); U = -2 p/|p| is the unit tangent in
+//   panel_far2's output scaling (it returns -ustar/2, -vstar/2)
+constexpr int kCoefRec = 3;
 __global__ void __launch_bounds__(256)
 pack_coeff_panels_kernel(int np, const float* __restrict__ nx, const float* __restrict__ ny,
                          const uint32_t* __restrict__ idx, const float* __restrict__ area,
@@ -39,9 +42,12 @@ pack_coeff_panels_kernel(int np, const float* __restrict__ nx, const float* __re
   const uint32_t i0 = idx[2 * j], i1 = idx[2 * j + 1];
   const float x0 = nx[i0], y0 = ny[i0], x1 = nx[i1], y1 = ny[i1];
   const float px = x1 - x0, py = y1 - y0;
-  packed[2 * j] = make_float4(x0, y0, px, py);
+  const float hx = -0.5f * px, hy = -0.5f * py;
+  const float rlen = 1.0f / sqrtf(px * px + py * py);
+  packed[kCoefRec * j] = make_float4(x0, y0, hx, hy);
   // collocation point as the reference forms it: 0.5*(x1+x0) (src/Coefficients.h:327-328,356)
-  packed[2 * j + 1] = make_float4(0.5f * (x1 + x0), 0.5f * (y1 + y0), area[j], 1.0f / sqrtf(px * px + py * py));
+  packed[kCoefRec * j + 1] = make_float4(0.5f * (x1 + x0), 0.5f * (y1 + y0), area[j], (hx * hx + hy * hy) * (1.0f / kFarZeta2));
+  packed[kCoefRec * j + 2] = make_float4(-2.0f * (px * rlen), -2.0f * (py * rlen), 0.0f, 0.0f);
 }
 
 struct CoefArgs {
@@ -54,60 +60,74 @@ struct CoefArgs {
   float* coeffs;
 };
 
-// unit-strength vortex velocity (vu, vv) of panel {x0,y0,px,py,1/len} at (tx,ty);
-// the unit source velocity is (vv, -vu) (src/Kernels.h:447-456 with vs = ss = 1)
-__device__ __forceinline__ void unit_panel_vel(const float4 G, float rlen, float tx, float ty, float& vu, float& vv) {
-  float ustar, vstar;
-  panel_pair(G.x, G.y, G.z, G.w, tx, ty, ustar, vstar);
-  const float ux = G.z * rlen, uy = G.w * rlen;
-  vu = ustar * ux - vstar * uy;
-  vv = ustar * uy + vstar * ux;
-}
-
+// One (target panel i, source panel j) pair needs TWO unit-strength panel velocities -- panel j on the centre of
+// panel i and, for the two-way average, panel i on the centre of panel j -- and they are the two lanes of the
+// packed arithmetic: lane x = (vu, vv) of j on i, lane y = (wu, wv) of i on j.  The unit source velocity is
+// (vv, -vu) (src/Kernels.h:447-456 with vs = ss = 1).
 template <bool BOTH>
 __global__ void __launch_bounds__(kCoefThreads)
 coeff_kernel(const CoefArgs a) {
-  __shared__ float4 s[2 * kCoefSrcTile];
+  __shared__ float4 s[kCoefRec * kCoefSrcTile];
   const int tid = threadIdx.x;
   const int i = blockIdx.x * kCoefThreads + tid;
   const int j0 = blockIdx.y * kCoefSrcTile;
   const int nj = min(kCoefSrcTile, a.nsrc - j0);
-  for (int k = tid; k < 2 * nj; k += kCoefThreads) s[k] = a.spack[2 * (size_t)j0 + k];
+  for (int k = tid; k < kCoefRec * nj; k += kCoefThreads) s[k] = a.spack[kCoefRec * (size_t)j0 + k];
   __syncthreads();
-  if (i >= a.ntarg) return;
-  const float4 T = a.tpack[2 * (size_t)i];
-  const float4 Tc = a.tpack[2 * (size_t)i + 1];
-  const float ttx = a.ttx[i], tty = a.tty[i];
-  const float tnx = BOTH ? a.tnx[i] : 0.0f, tny = BOTH ? a.tny[i] : 0.0f;
+  // threads past the last target keep computing on a copy of it (the warp votes in the loop need every lane)
+  const int ii = min(i, a.ntarg - 1);
+  const float4 T = a.tpack[kCoefRec * (size_t)ii];
+  const float4 Tc = a.tpack[kCoefRec * (size_t)ii + 1];
+  const float4 Tu = a.tpack[kCoefRec * (size_t)ii + 2];
+  const float ttx = a.ttx[ii], tty = a.tty[ii];
+  const float2 T1 = f2(ttx, BOTH ? a.tnx[ii] : 0.0f);     // {tangent.x, normal.x}
+  const float2 T2 = f2(tty, BOTH ? a.tny[ii] : 0.0f);     // {tangent.y, normal.y}
   const float rta = 1.0f / Tc.z;
   const float fac = (float)(1.0 / (2.0 * 3.14159265358979323846));   // "const S fac = 1.0/(2.0*M_PI)"
+  const float hfac = 0.5f * fac;                                     // exact scaling: (0.5 c) fac == c (0.5 fac)
+  const float pifac = 3.14159265358979323846f * fac;
   for (int jj = 0; jj < nj; ++jj) {
     const int j = j0 + jj;
-    const float4 S = s[2 * jj];
-    const float4 Sc = s[2 * jj + 1];
-    float vu, vv, wu, wv;
-    unit_panel_vel(S, Sc.w, Tc.x, Tc.y, vu, vv);      // panel j on the centre of panel i
-    unit_panel_vel(T, Tc.w, Sc.x, Sc.y, wu, wv);      // panel i on the centre of panel j ("two way")
-    const float fact = Sc.z * rta;                    // sa[j]/ta[i]
+    const float4 S = s[kCoefRec * jj];
+    const float4 Sc = s[kCoefRec * jj + 1];
+    const float4 Su = s[kCoefRec * jj + 2];
+    const float2 Hx = f2(S.z, T.z), Hy = f2(S.w, T.w);
+    const float2 ex = add2(add2(f2(Tc.x, Sc.x), neg2(f2(S.x, T.x))), Hx);
+    const float2 ey = add2(add2(f2(Tc.y, Sc.y), neg2(f2(S.y, T.y))), Hy);
+    float2 rr, ri, e2;
+    panel_far2(ex, ey, Hx, Hy, rr, ri, e2);
+    const bool na = !(e2.x > Sc.w), nb = !(e2.y > Tc.w);
+    if (__any_sync(0xffffffffu, na || nb)) {
+      float us, vs;
+      panel_pair(S.x, S.y, -2.0f * S.z, -2.0f * S.w, Tc.x, Tc.y, us, vs);
+      if (na) { ri.x = -0.5f * us; rr.x = -0.5f * vs; }
+      panel_pair(T.x, T.y, -2.0f * T.z, -2.0f * T.w, Sc.x, Sc.y, us, vs);
+      if (nb) { ri.y = -0.5f * us; rr.y = -0.5f * vs; }
+    }
+    const float2 Ux = f2(Su.x, Tu.x), Uy = f2(Su.y, Tu.y);
+    const float2 vu2 = fma2(ri, Ux, neg2(mul2(rr, Uy)));   // {vu, wu}
+    const float2 vv2 = fma2(ri, Uy, mul2(rr, Ux));         // {vv, wv}
+    const float fact = Sc.z * rta;                         // sa[j]/ta[i]
     const bool self = a.same && (i == j);
+    if (i >= a.ntarg) continue;
     if (BOTH) {
-      float c1e1 = vu * ttx + vv * tty;
-      float c1e2 = vu * tnx + vv * tny;
-      float c2e1 = vv * ttx - vu * tty;               // source velocity = (vv, -vu)
-      float c2e2 = vv * tnx - vu * tny;
-      c1e1 = 0.5f * (c1e1 - fact * (wu * ttx + wv * tty));
-      c1e2 = 0.5f * (c1e2 - fact * (wu * tnx + wv * tny));
-      c2e1 = 0.5f * (c2e1 - fact * (wv * ttx - wu * tty));
-      c2e2 = 0.5f * (c2e2 - fact * (wv * tnx - wu * tny));
-      if (self) { c1e1 = 3.14159265358979323846f; c1e2 = 0.0f; c2e1 = 0.0f; c2e2 = 3.14159265358979323846f; }
+      // {c1e1, c1e2} = vortex column on {tangent, normal}; {c2e1, c2e2} = source column
+      float2 c1 = fma2(f2(vu2.x), T1, mul2(f2(vv2.x), T2));
+      float2 c2 = fma2(f2(vv2.x), T1, neg2(mul2(f2(vu2.x), T2)));
+      const float2 w1 = fma2(f2(vu2.y), T1, mul2(f2(vv2.y), T2));
+      const float2 w2 = fma2(f2(vv2.y), T1, neg2(mul2(f2(vu2.y), T2)));
+      c1 = mul2(fma2(f2(-fact), w1, c1), f2(hfac));
+      c2 = mul2(fma2(f2(-fact), w2, c2), f2(hfac));
+      if (self) { c1 = f2(pifac, 0.0f); c2 = f2(0.0f, pifac); }
       float2* col1 = reinterpret_cast<float2*>(a.coeffs + (size_t)(2 * j) * a.ld) + i;
       float2* col2 = reinterpret_cast<float2*>(a.coeffs + (size_t)(2 * j + 1) * a.ld) + i;
-      *col1 = make_float2(c1e1 * fac, c1e2 * fac);
-      *col2 = make_float2(c2e1 * fac, c2e2 * fac);
+      *col1 = c1;
+      *col2 = c2;
     } else {
-      float c = 0.5f * ((vu * ttx + vv * tty) - fact * (wu * ttx + wv * tty));
-      if (self) c = 3.14159265358979323846f;
-      a.coeffs[(size_t)j * a.ld + i] = c * fac;
+      const float2 t2 = fma2(vu2, f2(ttx), mul2(vv2, f2(tty)));
+      float c = hfac * fmaf(-fact, t2.y, t2.x);
+      if (self) c = pifac;
+      a.coeffs[(size_t)j * a.ld + i] = c;
     }
   }
 }
@@ -118,9 +138,9 @@ static int coeff_device(o2d_context* c, int nsrc, const float* snx, const float*
                         const float* sarea, int ntarg, const float* tnx_, const float* tny_, const uint32_t* tidx,
                         const float* tarea, const float* ttx, const float* tty, const float* tnx, const float* tny,
                         int both, int same, size_t ld, float* coeffs) {
-  CU(c->panel_packed.reserve(((size_t)nsrc + (size_t)ntarg) * 32));
+  CU(c->panel_packed.reserve(((size_t)nsrc + (size_t)ntarg) * (16 * kCoefRec)));
   float4* spack = c->panel_packed.as<float4>();
-  float4* tpack = spack + 2 * (size_t)nsrc;
+  float4* tpack = spack + kCoefRec * (size_t)nsrc;
   pack_coeff_panels_kernel<<<(nsrc + 255) / 256, 256, 0, c->stream>>>(nsrc, snx, sny, sidx, sarea, spack);
   CU(cudaGetLastError());
   pack_coeff_panels_kernel<<<(ntarg + 255) / 256, 256, 0, c->stream>>>(ntarg, tnx_, tny_, tidx, tarea, tpack);

@@ -40,7 +40,7 @@ struct PPArgs {
 };
 
 struct PanelArgs {
-  const float4* packed;   // 2 float4 per panel: {x0,y0,x1,y1} {a,b,-,-}
+  const float4* packed;   // 4 float4 per panel PAIR (layout: pack_panels_kernel)
   int npanels_padded;     // multiple of kPanelTile
   int tiles_per_chunk;
   const float* tx;
@@ -81,7 +81,8 @@ cudaError_t launch_pack_sources(int mode, int ns, const float* sx, const float* 
 cudaError_t launch_pack_panels(int np, const float* nx, const float* ny, const uint32_t* idx,
                                const float* vs, const float* ss, float4* packed, int np_padded,
                                cudaStream_t st);
-cudaError_t launch_panels_on_points(const PanelArgs& a, int nchunks, cudaStream_t st);
+// rpt: targets per thread (1 or 2); grid.x covers 128*rpt targets per CTA
+cudaError_t launch_panels_on_points(const PanelArgs& a, int nchunks, int rpt, cudaStream_t st);
 cudaError_t launch_panels_combine(const double* partial, int nchunks, int nt, const OutPtrs& out, cudaStream_t st);
 // points-on-panels: targets are panels (one per thread), sources are packed particles
 struct PtPanArgs {
@@ -98,7 +99,7 @@ cudaError_t launch_points_on_panels(const PtPanArgs& a, int nchunks, cudaStream_
 cudaError_t launch_ptpan_combine_geom(const double* partial, int nchunks, const PtPanArgs& a, cudaStream_t st);
 // out[2][np] = sum over chunks of partial[chunk][2][np] (zeros when nchunks == 0)
 cudaError_t launch_ptpan_reduce_chunks(const double* partial, int nchunks, int np, double* out, cudaStream_t st);
-int panels_occupancy();
+int panels_occupancy(int rpt);
 int ptpan_occupancy();
 
 // elementwise helpers

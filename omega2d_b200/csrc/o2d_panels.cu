@@ -26,74 +26,131 @@ namespace o2d {
 
 // ---- packing: gather node coordinates through idx once (the reference gathers per pair,
 // src/Influence.h:561-562) ---------------------------------------------------------------------------
+// One thread per PAIR of panels (A = 2q, B = 2q+1); 4 float4 per pair so that every operand of the
+// packed-lane arithmetic is one 8-byte half of an LDS.128:
+//   {x0A x0B y0A y0B} {HxA HxB HyA HyB} {aA aB bA bB} {thrA thrB - -}
+// H = -p/2 (p = node1 - node0), a,b = the strength-weighted unit tangent of the header comment times -2
+// (panel_far2 returns -ustar/2, -vstar/2), thr = |H|^2 / kFarZeta2: a target with |t - centre|^2 <= thr takes
+// the general panel_pair().
 __global__ void __launch_bounds__(256)
 pack_panels_kernel(int np, const float* __restrict__ nx, const float* __restrict__ ny,
                    const uint32_t* __restrict__ idx, const float* __restrict__ vs,
                    const float* __restrict__ ss, float4* __restrict__ packed, int np_padded) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= np_padded) return;
-  const int jj = j < np ? j : np - 1;
-  const uint32_t i0 = idx[2 * jj], i1 = idx[2 * jj + 1];
-  const float x0 = nx[i0], y0 = ny[i0];
-  const float px = nx[i1] - x0, py = ny[i1] - y0;
-  const float mult = 1.0f / sqrtf(px * px + py * py);   // my_rsqrt(panl), src/Kernels.h:385
-  const float v = j < np ? vs[jj] : 0.0f;
-  const float s = (j < np && ss != nullptr) ? ss[jj] : 0.0f;
-  const float a = (v * px + s * py) * mult;
-  const float b = (v * py - s * px) * mult;
-  packed[2 * j]     = make_float4(x0, y0, px, py);
-  packed[2 * j + 1] = make_float4(a, b, 0.0f, 0.0f);
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (2 * q >= np_padded) return;
+  float x0[2], y0[2], hx[2], hy[2], a[2], b[2], thr[2];
+#pragma unroll
+  for (int l = 0; l < 2; ++l) {
+    const int j = 2 * q + l;
+    const int jj = j < np ? j : np - 1;
+    const uint32_t i0 = idx[2 * jj], i1 = idx[2 * jj + 1];
+    x0[l] = nx[i0]; y0[l] = ny[i0];
+    const float px = nx[i1] - x0[l], py = ny[i1] - y0[l];
+    const float mult = 1.0f / sqrtf(px * px + py * py);   // my_rsqrt(panl), src/Kernels.h:385
+    const float v = j < np ? vs[jj] : 0.0f;
+    const float s = (j < np && ss != nullptr) ? ss[jj] : 0.0f;
+    a[l] = -2.0f * ((v * px + s * py) * mult);
+    b[l] = -2.0f * ((v * py - s * px) * mult);
+    hx[l] = -0.5f * px; hy[l] = -0.5f * py;
+    thr[l] = (hx[l] * hx[l] + hy[l] * hy[l]) * (1.0f / kFarZeta2);
+  }
+  packed[4 * q]     = make_float4(x0[0], x0[1], y0[0], y0[1]);
+  packed[4 * q + 1] = make_float4(hx[0], hx[1], hy[0], hy[1]);
+  packed[4 * q + 2] = make_float4(a[0], a[1], b[0], b[1]);
+  packed[4 * q + 3] = make_float4(thr[0], thr[1], 0.0f, 0.0f);
 }
 
 cudaError_t launch_pack_panels(int np, const float* nx, const float* ny, const uint32_t* idx,
                                const float* vs, const float* ss, float4* packed, int np_padded,
                                cudaStream_t st) {
   if (np_padded <= 0) return cudaSuccess;
-  pack_panels_kernel<<<(np_padded + 255) / 256, 256, 0, st>>>(np, nx, ny, idx, vs, ss, packed, np_padded);
+  const int nq = np_padded / 2;
+  pack_panels_kernel<<<(nq + 255) / 256, 256, 0, st>>>(np, nx, ny, idx, vs, ss, packed, np_padded);
   return cudaGetLastError();
 }
 
 // ---- panels on points --------------------------------------------------------------------------------
+// A thread owns R targets; a packed lane pair is TWO PANELS against one target.
 constexpr int kPanThreads = 128;
 
+// general (near-field) pair for the lanes that need it; result in panel_far2's scaling
+__device__ __forceinline__ void near_fix(bool nx_, bool ny_, float x0a, float y0a, float hxa, float hya,
+                                         float x0b, float y0b, float hxb, float hyb, float tx, float ty,
+                                         float2& rr, float2& ri) {
+  float us, vs;
+  panel_pair(x0a, y0a, -2.0f * hxa, -2.0f * hya, tx, ty, us, vs);
+  if (nx_) { ri.x = -0.5f * us; rr.x = -0.5f * vs; }
+  panel_pair(x0b, y0b, -2.0f * hxb, -2.0f * hyb, tx, ty, us, vs);
+  if (ny_) { ri.y = -0.5f * us; rr.y = -0.5f * vs; }
+}
+
+template <int R>
 __global__ void __launch_bounds__(kPanThreads)
 panels_on_points_kernel(const PanelArgs a) {
-  __shared__ float4 s[2 * kPanelTile];
+  __shared__ float4 s[2 * kPanelTile];   // kPanelTile/2 panel pairs x 4 float4
   const int tid = threadIdx.x;
-  const int i = blockIdx.x * kPanThreads + tid;
-  const bool ok = i < a.nt;
-  const float tx = ok ? a.tx[i] : 1.0e6f;
-  const float ty = ok ? a.ty[i] : 1.0e6f;
+  const int base = blockIdx.x * (kPanThreads * R) + tid;
+  float tx[R], ty[R];
+  double accu[R], accv[R];
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    const int i = base + k * kPanThreads;
+    const bool ok = i < a.nt;
+    tx[k] = ok ? a.tx[i] : 1.0e6f;
+    ty[k] = ok ? a.ty[i] : 1.0e6f;
+    accu[k] = 0.0; accv[k] = 0.0;
+  }
   const int ntiles_all = a.npanels_padded / kPanelTile;
   const int tile_begin = blockIdx.y * a.tiles_per_chunk;
   const int tile_end = min(tile_begin + a.tiles_per_chunk, ntiles_all);
-  double accu = 0.0, accv = 0.0;
   for (int t = tile_begin; t < tile_end; ++t) {
     __syncthreads();
     const float4* g = a.packed + (size_t)t * (2 * kPanelTile);
     for (int k = tid; k < 2 * kPanelTile; k += kPanThreads) s[k] = g[k];
     __syncthreads();
-    float pu = 0.0f, pv = 0.0f;
+    float2 pu[R], pv[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) { pu[k] = f2(0.0f); pv[k] = f2(0.0f); }
 #pragma unroll 2
-    for (int j = 0; j < kPanelTile; ++j) {
-      const float4 G = s[2 * j];
-      const float4 H = s[2 * j + 1];
-      float ustar, vstar;
-      panel_pair(G.x, G.y, G.z, G.w, tx, ty, ustar, vstar);
-      pu = fmaf(ustar, H.x, pu);  pu = fmaf(-vstar, H.y, pu);
-      pv = fmaf(ustar, H.y, pv);  pv = fmaf(vstar, H.x, pv);
+    for (int q = 0; q < kPanelTile / 2; ++q) {
+      const float4 P = s[4 * q];        // x0A x0B y0A y0B
+      const float4 H = s[4 * q + 1];    // HxA HxB HyA HyB
+      const float4 S = s[4 * q + 2];    // aA aB bA bB
+      const float4 T = s[4 * q + 3];    // thrA thrB
+      const float2 Hx = f2(H.x, H.y), Hy = f2(H.z, H.w);
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        // e = (t - node0) + H: the subtraction first, so it is exact for nearby targets as in the reference
+        const float2 ex = add2(add2(f2(tx[k]), neg2(f2(P.x, P.y))), Hx);
+        const float2 ey = add2(add2(f2(ty[k]), neg2(f2(P.z, P.w))), Hy);
+        float2 rr, ri, e2;
+        panel_far2(ex, ey, Hx, Hy, rr, ri, e2);
+        const bool na = !(e2.x > T.x), nb = !(e2.y > T.y);   // also true for NaN
+        if (__any_sync(0xffffffffu, na || nb))
+          near_fix(na, nb, P.x, P.z, H.x, H.z, P.y, P.w, H.y, H.w, tx[k], ty[k], rr, ri);
+        const float2 A = f2(S.x, S.y), B = f2(S.z, S.w);
+        pu[k] = fma2(ri, A, pu[k]);  pu[k] = fma2(neg2(rr), B, pu[k]);
+        pv[k] = fma2(ri, B, pv[k]);  pv[k] = fma2(rr, A, pv[k]);
+      }
     }
-    accu += (double)pu;
-    accv += (double)pv;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      accu[k] += (double)pu[k].x + (double)pu[k].y;
+      accv[k] += (double)pv[k].x + (double)pv[k].y;
+    }
   }
-  if (!ok) return;
-  if (a.partial == nullptr) {
-    a.out.p[0][i] = (float)((double)a.out.p[0][i] + accu);
-    a.out.p[1][i] = (float)((double)a.out.p[1][i] + accv);
-  } else {
-    double* dst = a.partial + ((size_t)blockIdx.y * 2) * (size_t)a.nt + i;
-    dst[0] = accu;
-    dst[a.nt] = accv;
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    const int i = base + k * kPanThreads;
+    if (i >= a.nt) continue;
+    if (a.partial == nullptr) {
+      a.out.p[0][i] = (float)((double)a.out.p[0][i] + accu[k]);
+      a.out.p[1][i] = (float)((double)a.out.p[1][i] + accv[k]);
+    } else {
+      double* dst = a.partial + ((size_t)blockIdx.y * 2) * (size_t)a.nt + i;
+      dst[0] = accu[k];
+      dst[a.nt] = accv[k];
+    }
   }
 }
 
@@ -111,18 +168,22 @@ panels_combine_kernel(const double* __restrict__ partial, int nchunks, int nt, c
   out.p[1][i] = (float)((double)out.p[1][i] + v);
 }
 
-cudaError_t launch_panels_on_points(const PanelArgs& a, int nchunks, cudaStream_t st) {
-  dim3 grid((a.nt + kPanThreads - 1) / kPanThreads, nchunks, 1);
-  panels_on_points_kernel<<<grid, kPanThreads, 0, st>>>(a);
+cudaError_t launch_panels_on_points(const PanelArgs& a, int nchunks, int rpt, cudaStream_t st) {
+  dim3 grid((a.nt + kPanThreads * rpt - 1) / (kPanThreads * rpt), nchunks, 1);
+  if (rpt == 2) panels_on_points_kernel<2><<<grid, kPanThreads, 0, st>>>(a);
+  else          panels_on_points_kernel<1><<<grid, kPanThreads, 0, st>>>(a);
   return cudaGetLastError();
 }
 cudaError_t launch_panels_combine(const double* partial, int nchunks, int nt, const OutPtrs& out, cudaStream_t st) {
   panels_combine_kernel<<<(nt + 255) / 256, 256, 0, st>>>(partial, nchunks, nt, out);
   return cudaGetLastError();
 }
-int panels_occupancy() {
+int panels_occupancy(int rpt) {
   int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, panels_on_points_kernel, kPanThreads, 0) != cudaSuccess) return 1;
+  const cudaError_t e = rpt == 2
+      ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, panels_on_points_kernel<2>, kPanThreads, 0)
+      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, panels_on_points_kernel<1>, kPanThreads, 0);
+  if (e != cudaSuccess) return 1;
   return nb > 0 ? nb : 1;
 }
 
@@ -143,25 +204,39 @@ points_on_panels_kernel(const PtPanArgs a) {
   }
   const int tile_begin = blockIdx.y * a.tiles_per_chunk;
   const int tile_end = min(tile_begin + a.tiles_per_chunk, a.ntiles);
+  // far-field form (panel_far2) with the roles mirrored: e' = centre - t = (node0 - t) + p/2 and H' = +p/2 give
+  // the same zeta'; a packed lane pair is TWO PARTICLES against this thread's panel
+  const float2 Hx = f2(0.5f * px), Hy = f2(0.5f * py);
+  const float thr = (Hx.x * Hx.x + Hy.x * Hy.x) * (1.0f / kFarZeta2);
   double acc1 = 0.0, acc2 = 0.0;
   for (int t = tile_begin; t < tile_end; ++t) {
     __syncthreads();
     const float4* g = a.packed_src + (size_t)t * kTile;
     for (int k = tid; k < kTile; k += kPtPanThreads) s[k] = g[k];
     __syncthreads();
-    float p1 = 0.0f, p2 = 0.0f;
+    float2 p1 = f2(0.0f), p2 = f2(0.0f);
 #pragma unroll 2
     for (int p = 0; p < kTile / 2; ++p) {
       const float4 A = s[2 * p];      // -x0 -x1 -y0 -y1 of two particles
       const float4 B = s[2 * p + 1];  // s0 s1 . .
-      float ustar, vstar;
-      panel_pair(x0, y0, px, py, -A.x, -A.z, ustar, vstar);
-      p1 = fmaf(B.x, ustar, p1);  p2 = fmaf(B.x, vstar, p2);
-      panel_pair(x0, y0, px, py, -A.y, -A.w, ustar, vstar);
-      p1 = fmaf(B.y, ustar, p1);  p2 = fmaf(B.y, vstar, p2);
+      const float2 ex = add2(add2(f2(A.x, A.y), f2(x0)), Hx);
+      const float2 ey = add2(add2(f2(A.z, A.w), f2(y0)), Hy);
+      float2 rr, ri, e2;
+      panel_far2(ex, ey, Hx, Hy, rr, ri, e2);
+      const bool na = !(e2.x > thr), nb = !(e2.y > thr);
+      if (__any_sync(0xffffffffu, na || nb)) {
+        float us, vs;
+        panel_pair(x0, y0, px, py, -A.x, -A.z, us, vs);
+        if (na) { ri.x = -0.5f * us; rr.x = -0.5f * vs; }
+        panel_pair(x0, y0, px, py, -A.y, -A.w, us, vs);
+        if (nb) { ri.y = -0.5f * us; rr.y = -0.5f * vs; }
+      }
+      const float2 S = f2(B.x, B.y);
+      p1 = fma2(S, ri, p1);
+      p2 = fma2(S, rr, p2);
     }
-    acc1 += (double)p1;
-    acc2 += (double)p2;
+    acc1 += -2.0 * ((double)p1.x + (double)p1.y);
+    acc2 += -2.0 * ((double)p2.x + (double)p2.y);
   }
   if (!ok) return;
   if (a.partial == nullptr) {

@@ -358,3 +358,50 @@ def test_points_status_reductions(n, ctx, port):
     if n:
         d = [torch.from_numpy(a).cuda() for a in (x, y, s)]
         assert ctx.points_status(o2d.MEM_DEVICE, n, *d) == got                        # device path, bit-reproducible
+
+
+def _ring_targets(cx, cy, length, nrho=240, nphi=48, lo=-1.5, hi=2.5):
+    """Targets on rings around (cx, cy) at 10**lo .. 10**hi panel lengths: covers the general pair, the far-field
+    series (beyond 3.16 panel lengths, panel_far2 in o2d_device.cuh) and the switch between them."""
+    rho = np.logspace(lo, hi, nrho)[:, None] * length
+    phi = (np.arange(nphi) + 0.37) * (2 * np.pi / nphi)
+    return (cx + rho * np.cos(phi)[None, :]).astype(np.float32).ravel(), (cy + rho * np.sin(phi)[None, :]).astype(np.float32).ravel()
+
+
+@pytest.mark.parametrize("length,angle", [(0.01, 0.3), (0.00123, 2.1), (0.2, -1.0)])
+def test_panel_near_far_transition_pointwise(length, angle, ctx):
+    """ONE panel, vortex + source strength: every target separately within 3e-6 of exact (float64) arithmetic,
+    relative to the local velocity magnitude (the reference's own float32 form is up to 1e-4 off here)."""
+    from f64ref import panels_on_points_f64
+    nx = np.array([0.3, 0.3 + length * np.cos(angle)], np.float32)
+    ny = np.array([0.2, 0.2 + length * np.sin(angle)], np.float32)
+    idx = np.array([0, 1], np.uint32)
+    vs = np.array([0.8], np.float32); ss = np.array([-0.6], np.float32)
+    tx, ty = _ring_targets(0.5 * (float(nx[0]) + float(nx[1])), 0.5 * (float(ny[0]) + float(ny[1])), length)
+    u, v = ctx.panels_on_points_np(nx, ny, idx, vs, ss, tx, ty)
+    eu, ev = panels_on_points_f64(nx, ny, idx, vs, ss, tx, ty)
+    err = np.hypot(u - eu, v - ev) / np.hypot(eu, ev)
+    assert err.max() < 3e-6, (err.max(), np.argmax(err))
+
+
+def test_points_on_panels_near_far_transition_pointwise(ctx):
+    """ONE particle against many panels of different length, orientation and distance: each panel's velocity is a
+    single pair, so the check is pointwise.  Exact = float64."""
+    from f64ref import points_on_panels_f64
+    rng = np.random.default_rng(11)
+    npan = 6000
+    length = 10 ** rng.uniform(-3, -1, npan)
+    ang = rng.uniform(0, 2 * np.pi, npan)
+    rho = 10 ** rng.uniform(-1.0, 2.0, npan) * length
+    phi = rng.uniform(0, 2 * np.pi, npan)
+    cx, cy = 0.1 + rho * np.cos(phi), -0.2 + rho * np.sin(phi)       # panel centres around the particle
+    nx = np.empty(2 * npan, np.float32); ny = np.empty(2 * npan, np.float32)
+    nx[0::2] = cx - 0.5 * length * np.cos(ang); nx[1::2] = cx + 0.5 * length * np.cos(ang)
+    ny[0::2] = cy - 0.5 * length * np.sin(ang); ny[1::2] = cy + 0.5 * length * np.sin(ang)
+    idx = np.arange(2 * npan, dtype=np.uint32)
+    area = np.hypot(nx[1::2] - nx[0::2], ny[1::2] - ny[0::2]).astype(np.float32)
+    sx = np.array([0.1], np.float32); sy = np.array([-0.2], np.float32); s = np.array([1.3], np.float32)
+    pu, pv = ctx.points_on_panels_np(sx, sy, s, nx, ny, idx, area)
+    eu, ev = points_on_panels_f64(sx, sy, s, nx, ny, idx, area)
+    err = np.hypot(pu - eu, pv - ev) / np.hypot(eu, ev)
+    assert err.max() < 3e-6, (err.max(), np.argmax(err))
