@@ -235,13 +235,27 @@ int o2d_panels_on_panels_coeff(o2d_context* ctx, int mem,
  *   num_moved: if non-NULL receives the number of pushes (the reference's "pushed N particles")
  * Every particle closer than cutoff_mult*ips (minus 0.001 ips) to the surface along the mean normal of
  * its closest panel(s)/node(s) is moved onto that layer; the search repeats for moved particles until
- * none moves (corners).  method 0 (strength cropping with the diffusion cut tables) returns
- * O2D_ERR_UNSUPPORTED.
+ * none moves (corners).  method 0 (strength cropping with the cut tables, src/Reflect.h:392-480,
+ * :668-690) has no caller anywhere in the reference and returns O2D_ERR_UNSUPPORTED.
  */
 int o2d_clear_inner_layer(o2d_context* ctx, int method, int mem,
                           int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
                           const float* snx, const float* sny,
                           int n, float* tx, float* ty, float cutoff_mult, float ips, long long* num_moved);
+
+/*
+ * Mirror particles that ended up inside a body back to the outside.  Replaces reflect_panp2<S>
+ * (reference src/Reflect.h:174-350) as called by reflect_interior<S> (:357-380) for one Surfaces
+ * boundary and one Points collection -- what Diffusion::step does before VRM, which "only works in
+ * free space" (src/Diffusion.h:299-301).  Same panel and point arguments as o2d_clear_inner_layer.
+ * For each particle: closest panel(s)/node(s) (exact ties averaged), mean normal and mean contact
+ * point cp; if (x - cp).normal < 0 the particle is moved to cp + dist*normal.  One pass (no re-test).
+ *   num_reflected: if non-NULL receives the reference's "reflected N particles" count.
+ */
+int o2d_reflect_interior(o2d_context* ctx, int mem,
+                         int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                         const float* snx, const float* sny,
+                         int n, float* tx, float* ty, long long* num_reflected);
 
 /* ---- status reductions ----------------------------------------------------------------------- */
 

@@ -82,6 +82,7 @@ def load_library() -> C.CDLL:
                                                i, i, C.c_longlong, vp]
     lib.o2d_clear_inner_layer.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp, i, vp, vp, C.c_float, C.c_float,
                                           C.POINTER(C.c_longlong)]
+    lib.o2d_reflect_interior.argtypes = [vp, i, i, i, vp, vp, vp, vp, vp, i, vp, vp, C.POINTER(C.c_longlong)]
     lib.o2d_find_vels_sharded.argtypes = [vp, i, i, i, i, i, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp,
                                           i, vp, vp, vp, vp, vp, vp, d, d]
     lib.o2d_points_on_panels_sharded.argtypes = [vp, i, i, vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp]
@@ -254,6 +255,13 @@ class Context:
             int(n), _ptr(tx), _ptr(ty), float(cutoff_mult), float(ips), C.byref(moved) if want_count else None))
         return moved.value
 
+    def reflect_interior(self, mem, np_, nnodes, nx, ny, idx, snx, sny, n, tx, ty, want_count=True):
+        moved = C.c_longlong(0)
+        self._check(self.lib.o2d_reflect_interior(
+            self._h, int(mem), int(np_), int(nnodes), _ptr(nx), _ptr(ny), _ptr(idx), _ptr(snx), _ptr(sny),
+            int(n), _ptr(tx), _ptr(ty), C.byref(moved) if want_count else None))
+        return moved.value
+
     def find_vels_sharded(self, core, results, mem, nv_local, nv_block, vx, vy, vs, vr, np_, nnodes, nx, ny, idx,
                           pvs, pss, nt, tx, ty, tr, tu, tv, tq=None, fs=(0.0, 0.0)):
         core = CORE_ID[core] if isinstance(core, str) else int(core)
@@ -360,6 +368,13 @@ class Context:
         idx = np.ascontiguousarray(idx, dtype=np.uint32)
         x, y = np.array(x, np.float32), np.array(y, np.float32)
         moved = self.clear_inner_layer(1, MEM_HOST, snx.size, nx.size, nx, ny, idx, snx, sny, x.size, x, y, cutoff_mult, ips)
+        return x, y, moved
+
+    def reflect_interior_np(self, nx, ny, idx, snx, sny, x, y):
+        nx, ny, snx, sny = map(_f32, (nx, ny, snx, sny))
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        x, y = np.array(x, np.float32), np.array(y, np.float32)
+        moved = self.reflect_interior(MEM_HOST, snx.size, nx.size, nx, ny, idx, snx, sny, x.size, x, y)
         return x, y, moved
 
     def panels_on_points_np(self, nx, ny, idx, vs, ss, tx, ty, init=None):

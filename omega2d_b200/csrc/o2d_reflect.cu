@@ -1,4 +1,4 @@
-// o2d_reflect.cu -- clear_inner_layer, "push" method.
+// o2d_reflect.cu -- clear_inner_layer ("push" method) and reflect_interior.
 //
 // Replaces clear_inner_panp2<S> with _method == 1 (reference src/Reflect.h:490-733) as driven by
 // clear_inner_layer<S> (:735-768), which Convection runs on every Lagrangian collection after every
@@ -14,6 +14,11 @@
 // the reference's expressions imply (double pow, double contact point, double/float nextafter
 // overloads -- restated in oracle/o2d_oracle.c) are followed so that the closest-hit logic, which is
 // discontinuous, sees the same numbers: "new best" is distsq < mindist, a tie is distsq == mindist.
+//
+// reflect_interior<S> -> reflect_panp2<S> (src/Reflect.h:174-350, driver :357-380; Diffusion::step calls it
+// before VRM, src/Diffusion.h:301) is the same closest-element search run ONCE per particle with a
+// different ending: a particle on the inner side of its mean contact normal is mirrored to
+// cp + dist*normal.  It is the same kernel, template parameter MODE.
 #include "o2d_context.h"
 
 #include <cfloat>
@@ -61,6 +66,9 @@ struct CilArgs {
   unsigned long long* moved;
 };
 
+enum { MODE_PUSH = 1, MODE_REFLECT = 2 };
+
+template <int MODE>
 __global__ void __launch_bounds__(kCilThreads)
 clear_inner_kernel(const CilArgs a) {
   __shared__ float4 s[3 * kCilTile];
@@ -72,9 +80,11 @@ clear_inner_kernel(const CilArgs a) {
   unsigned int pushes = 0;
   for (int iter = 0; iter < a.max_iter; ++iter) {
     if (!__syncthreads_or(untested)) break;
-    float mindist = (float)(0.1 * (double)FLT_MAX);
+    // push: "0.1*numeric_limits<S>::max()" (src/Reflect.h:566); reflect: numeric_limits<S>::max() (:214)
+    float mindist = MODE == MODE_PUSH ? (float)(0.1 * (double)FLT_MAX) : FLT_MAX;
     int nhits = 0;
     float normx = 0.0f, normy = 0.0f, cpx = 0.0f, cpy = 0.0f;
+    float n0x = 0.0f, n0y = 0.0f, c0x = 0.0f, c0y = 0.0f;   // hits[0] (reflect's zero-normal fallback, :305-317)
     for (int j0 = 0; j0 < a.np; j0 += kCilTile) {
       const int nj = min(kCilTile, a.np - j0);
       __syncthreads();
@@ -104,21 +114,42 @@ clear_inner_kernel(const CilArgs a) {
         if (newbest || distsq == mindist) {
           if (newbest) { mindist = distsq; nhits = 0; normx = normy = cpx = cpy = 0.0f; }
           const float4 Nn = s[3 * j + 2];
+          float hnx, hny, hcx, hcy;
           if (kind == 0) {
             const float4 Np = s[3 * j + 1];
-            normx += Np.x; normy += Np.y;
-            cpx += (float)((1.0 - (double)t) * (double)P.x + (double)t * (double)P.z);
-            cpy += (float)((1.0 - (double)t) * (double)P.y + (double)t * (double)P.w);
+            hnx = Np.x; hny = Np.y;
+            hcx = (float)((1.0 - (double)t) * (double)P.x + (double)t * (double)P.z);
+            hcy = (float)((1.0 - (double)t) * (double)P.y + (double)t * (double)P.w);
           } else if (kind == 1) {
-            normx += Nn.x; normy += Nn.y; cpx += P.x; cpy += P.y;
+            hnx = Nn.x; hny = Nn.y; hcx = P.x; hcy = P.y;
           } else {
-            normx += Nn.z; normy += Nn.w; cpx += P.z; cpy += P.w;
+            hnx = Nn.z; hny = Nn.w; hcx = P.z; hcy = P.w;
           }
+          normx += hnx; normy += hny; cpx += hcx; cpy += hcy;
+          if (MODE == MODE_REFLECT && nhits == 0) { n0x = hnx; n0y = hny; c0x = hcx; c0y = hcy; }
           nhits++;
         }
       }
     }
-    if (untested) {
+    if (MODE == MODE_REFLECT) {
+      // reflect_panp2's ending (src/Reflect.h:291-342): one pass, no re-test
+      if (untested && nhits > 0) {
+        if (normx * normx + normy * normy == 0.0f) {   // opposing normals cancel: fall back to hits[0]
+          normx += n0x; normy += n0y; cpx = c0x; cpy = c0y;
+        }
+        const float normilen = (float)(1.0 / (double)sqrtf(normx * normx + normy * normy));
+        normx *= normilen; normy *= normilen;
+        cpx = __fdiv_rn(cpx, (float)nhits); cpy = __fdiv_rn(cpy, (float)nhits);
+        const float dotp = normx * (x - cpx) + normy * (y - cpy);
+        if (dotp < 0.0f) {
+          const float dist = sqrtf(mindist);           // hits[0].distsq == mindist
+          x = cpx + dist * normx;
+          y = cpy + dist * normy;
+          pushes++;
+        }
+      }
+      untested = false;
+    } else if (untested) {
       if (nhits == 0) {
         untested = false;   // "this messes up long runs, ignore it" (src/Reflect.h:620-622)
       } else {
@@ -145,7 +176,7 @@ clear_inner_kernel(const CilArgs a) {
 
 }  // namespace
 
-static int cil_device(o2d_context* c, int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+static int cil_device(o2d_context* c, int mode, int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
                       const float* snx, const float* sny, int n, float* tx, float* ty, float cutoff_mult, float ips,
                       unsigned long long* d_moved) {
   // scratch: node normals (2*nnodes floats) + packed panels (3 float4 each)
@@ -164,7 +195,9 @@ static int cil_device(o2d_context* c, int np, int nnodes, const float* nx, const
   a.cutoff = cutoff_mult * ips; a.ips = ips; a.max_iter = 1000; a.moved = d_moved;
   {
     PairTimer timer(c);
-    clear_inner_kernel<<<(n + kCilThreads - 1) / kCilThreads, kCilThreads, 0, c->stream>>>(a);
+    const int nb = (n + kCilThreads - 1) / kCilThreads;
+    if (mode == MODE_PUSH) clear_inner_kernel<MODE_PUSH><<<nb, kCilThreads, 0, c->stream>>>(a);
+    else                   clear_inner_kernel<MODE_REFLECT><<<nb, kCilThreads, 0, c->stream>>>(a);
     CU(cudaGetLastError());
   }
   c->launches += 3;
@@ -172,15 +205,12 @@ static int cil_device(o2d_context* c, int np, int nnodes, const float* nx, const
   return O2D_OK;
 }
 
-extern "C" int o2d_clear_inner_layer(o2d_context* c, int method, int mem,
-                                     int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
-                                     const float* snx, const float* sny,
-                                     int n, float* tx, float* ty, float cutoff_mult, float ips,
-                                     long long* num_moved) {
+static int cil_entry(o2d_context* c, int mode, int mem,
+                     int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                     const float* snx, const float* sny,
+                     int n, float* tx, float* ty, float cutoff_mult, float ips,
+                     long long* num_moved) {
   if (int rc = o2d_check_common(c, mem)) return rc;
-  if (method != 1)
-    return fail(O2D_ERR_UNSUPPORTED, "only the push method (1) is built; method 0 crops strengths with the "
-                                     "diffusion cut tables (reference src/Reflect.h:392-480), outside the convection path");
   if (np < 0 || nnodes < 0 || n < 0) return fail(O2D_ERR_INVALID, "negative count");
   if (num_moved) *num_moved = 0;
   if (np == 0 || n == 0) return O2D_OK;
@@ -190,7 +220,7 @@ extern "C" int o2d_clear_inner_layer(o2d_context* c, int method, int mem,
   CU(cudaMemsetAsync(d_moved, 0, sizeof(unsigned long long), c->stream));
   int rc;
   if (mem == O2D_MEM_DEVICE) {
-    if ((rc = cil_device(c, np, nnodes, nx, ny, idx, snx, sny, n, tx, ty, cutoff_mult, ips, d_moved))) return rc;
+    if ((rc = cil_device(c, mode, np, nnodes, nx, ny, idx, snx, sny, n, tx, ty, cutoff_mult, ips, d_moved))) return rc;
     if (num_moved) {   // the count is the only thing that needs the host: synchronous only when asked for
       unsigned long long h = 0;
       CU(cudaMemcpyAsync(&h, d_moved, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
@@ -211,7 +241,7 @@ extern "C" int o2d_clear_inner_layer(o2d_context* c, int method, int mem,
       (rc = o2d_h2d(c, dsny, sny, np)) || (rc = o2d_h2d(c, dtx, tx, n)) || (rc = o2d_h2d(c, dty, ty, n)))
     return rc;
   CU(cudaMemcpyAsync(c->hidx.p, idx, (size_t)2 * np * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-  if ((rc = cil_device(c, np, nnodes, dnx, dny, c->hidx.as<uint32_t>(), dsnx, dsny, n, dtx, dty, cutoff_mult, ips, d_moved)))
+  if ((rc = cil_device(c, mode, np, nnodes, dnx, dny, c->hidx.as<uint32_t>(), dsnx, dsny, n, dtx, dty, cutoff_mult, ips, d_moved)))
     return rc;
   unsigned long long h = 0;
   if ((rc = o2d_d2h(c, tx, dtx, n)) || (rc = o2d_d2h(c, ty, dty, n))) return rc;
@@ -219,4 +249,23 @@ extern "C" int o2d_clear_inner_layer(o2d_context* c, int method, int mem,
   CU(cudaStreamSynchronize(c->stream));
   if (num_moved) *num_moved = (long long)h;
   return O2D_OK;
+}
+
+extern "C" int o2d_clear_inner_layer(o2d_context* c, int method, int mem,
+                                     int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                                     const float* snx, const float* sny,
+                                     int n, float* tx, float* ty, float cutoff_mult, float ips,
+                                     long long* num_moved) {
+  if (int rc = o2d_check_common(c, mem)) return rc;
+  if (method != 1)
+    return fail(O2D_ERR_UNSUPPORTED, "only the push method (1) is built; method 0 (strength cropping with the cut "
+                                     "tables, reference src/Reflect.h:392-480,668-690) is never called by the reference");
+  return cil_entry(c, MODE_PUSH, mem, np, nnodes, nx, ny, idx, snx, sny, n, tx, ty, cutoff_mult, ips, num_moved);
+}
+
+extern "C" int o2d_reflect_interior(o2d_context* c, int mem,
+                                    int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                                    const float* snx, const float* sny,
+                                    int n, float* tx, float* ty, long long* num_reflected) {
+  return cil_entry(c, MODE_REFLECT, mem, np, nnodes, nx, ny, idx, snx, sny, n, tx, ty, 0.0f, 0.0f, num_reflected);
 }

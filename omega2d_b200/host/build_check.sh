@@ -24,6 +24,7 @@ if [ -d "$REF/src" ]; then
 #include "CoefficientsB200.h"
 #include "ReflectB200.h"
 void clear(std::vector<Collection>& b, std::vector<Collection>& v) { clear_inner_layer<float>(1, b, v, 0.2f, 0.02f); }
+void reflect(std::vector<Collection>& b, std::vector<Collection>& v) { reflect_interior<float>(b, v); }
 Vector<float> coeff_block(Collection& a, Collection& b) { return std::visit(CoefficientVisitor<float>(), a, b); }
 std::vector<float> rhs_block(Collection& a) { return std::visit(RHSVisitor<float>(), a); }
 void instantiate(std::vector<Collection>& a, std::vector<Collection>& b, std::vector<Collection>& c) {

@@ -252,6 +252,17 @@ class Port:
                   float(cutoff_factor), float(ips), int(max_iter))
         assert moved >= 0
         return x, y, int(moved)
+    def reflect_interior(self, nx, ny, idx, x, y):
+        """reflect_interior (reflect_panp2).  Returns new x, y and the number of reflected particles."""
+        nx, ny = map(_f32, (nx, ny)); idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        _, _, snx, sny, _ = self.panel_bases(nx, ny, idx)
+        x, y = np.array(x, np.float32), np.array(y, np.float32)
+        f = self.lib.o2d_oracle_reflect_interior
+        f.restype = C.c_longlong
+        f.argtypes = [C.c_int, C.c_int, _fp, _fp, _up, _fp, _fp, C.c_int, _fp, _fp]
+        moved = f(int(idx.size // 2), int(nx.size), _f(nx), _f(ny), _u(idx), _f(snx), _f(sny), int(x.size), _f(x), _f(y))
+        assert moved >= 0
+        return x, y, int(moved)
     def points_status(self, x, y, s):
         x, y, s = map(_f32, (x, y, s))
         out = [C.c_float() for _ in range(4)]
@@ -428,6 +439,28 @@ class Ref:
                float(cutoff_factor), float(ips))
         assert rc == 0
         return (x, y) if s is None else (x, y, s)
+    def reflect_interior(self, nx, ny, idx, x, y, s, r):
+        nx, ny = map(_f32, (nx, ny)); idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        x, y = np.array(x, np.float32), np.array(y, np.float32)
+        s, r = _f32(s), _f32(r)
+        f = self.lib.o2dref_reflect_interior
+        f.argtypes = [C.c_int, C.c_int, _fp, _fp, _up, C.c_int, _fp, _fp, _fp, _fp]
+        rc = f(int(idx.size // 2), int(nx.size), _f(nx), _f(ny), _u(idx), int(x.size), _f(x), _f(y), _f(s), _f(r))
+        assert rc == 0
+        return x, y
+    def write_vtk_points(self, directory, index, frameno, time, x, y, s, r, u, v, w=None):
+        """The reference's own Points::write_vtk.  Returns the bytes of the .vtu file it wrote and its name."""
+        x, y, u, v = map(_f32, (x, y, u, v))
+        s = None if s is None else _f32(s); r = None if r is None else _f32(r); w = None if w is None else _f32(w)
+        f = self.lib.o2dref_write_vtk_points
+        f.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_char_p, C.c_int]
+        buf = C.create_string_buffer(256)
+        rc = f(str(directory).encode(), int(index), int(frameno), float(time), int(x.size), _f(x), _f(y), _f(s), _f(r),
+               _f(u), _f(v), _f(w), buf, 256)
+        assert rc == 0, rc
+        name = buf.value.decode()
+        with open(os.path.join(str(directory), name), "rb") as fh:
+            return fh.read(), name
     def add_rot_strengths(self, nx, ny, idx, rotvel, vs, ss):
         """-> (vs, ss, (cx, cy)) from the reference's own body-bound Surfaces."""
         nx, ny = map(_f32, (nx, ny)); idx = np.ascontiguousarray(idx, dtype=np.uint32)

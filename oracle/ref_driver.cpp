@@ -465,6 +465,45 @@ int o2dref_clear_inner_layer(int method, int np, int nnodes, const float* nx, co
 }
 
 
+// reference reflect_interior<float> (src/Reflect.h:357-380 -> reflect_panp2 :174-350) on the reference's own
+// Collections: one Surfaces boundary, one Points collection; positions returned in place.
+int o2dref_reflect_interior(int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                            int n, float* x, float* y, const float* s, const float* r) {
+  StdoutMute mute;
+  std::vector<float> z((size_t)np, 0.0f);
+  std::vector<Collection> bdry, vort;
+  bdry.push_back(make_surfaces(np, nnodes, nx, ny, idx, z.data(), z.data()));
+  vort.push_back(make_points(n, x, y, s, r));
+  reflect_interior<float>(bdry, vort);
+  Points<float>& p = std::get<Points<float>>(vort[0]);
+  const auto& px = p.get_pos();
+  for (int i = 0; i < n; ++i) { x[i] = px[0][i]; y[i] = px[1][i]; }
+  return 0;
+}
+
+
+// reference Points<float>::write_vtk (src/Points.h:556-740; VtkXmlWriter.h, cppcodec base64, tinyxml2 printer) on
+// the reference's own Points: blobs (s != NULL: circulation + radius arrays) or inert field points; w != NULL
+// also engages the vorticity array.  The file is written into `dir` (the reference writes into the current
+// directory); its name (e.g. part_00_00007.vtu) is returned in fname.
+int o2dref_write_vtk_points(const char* dir, int index, int frameno, double time,
+                            int n, const float* x, const float* y, const float* s, const float* r,
+                            const float* u, const float* v, const float* w, char* fname, int fname_len) {
+  StdoutMute mute;
+  Points<float> p = make_points(n, x, y, s, r);
+  auto& pu = p.get_vel();
+  for (int i = 0; i < n; ++i) { pu[0][i] = u[i]; pu[1][i] = v[i]; }
+  if (w) { auto& pw = p.get_vort(); for (int i = 0; i < n; ++i) pw[i] = w[i]; }
+  char cwd[4096];
+  if (!getcwd(cwd, sizeof(cwd))) return -1;
+  if (chdir(dir) != 0) return -2;
+  const std::string name = p.write_vtk((size_t)index, (size_t)frameno, time);
+  if (chdir(cwd) != 0) return -3;
+  snprintf(fname, (size_t)fname_len, "%s", name.c_str());
+  return 0;
+}
+
+
 // reference Surfaces::add_rot_strengths_base (src/Surfaces.h:571-620) on a body-bound Surfaces attached to a
 // Body (so that the untransformed coordinates and the geometric centre exist, :623-676).  Returns the
 // geometric centre the reference derived in (cx, cy) and the updated strengths in vs, ss.

@@ -109,6 +109,17 @@ int main(int argc, char** argv) {
     const Points<float>& out = std::get<Points<float>>(near[0]);
     dump(f, out.get_pos()[0]); dump(f, out.get_pos()[1]);
   }
+  // reflect_interior on a copy of the particles pulled inside the body
+  {
+    std::vector<Collection> inside;
+    Points<float> shrunk = vortons;
+    for (size_t i = 0; i < nv; ++i) { shrunk.get_pos()[0][i] *= 0.6f; shrunk.get_pos()[1][i] *= 0.6f; }
+    dump(f, shrunk.get_pos()[0]); dump(f, shrunk.get_pos()[1]);
+    inside.push_back(shrunk);
+    reflect_interior<float>(bdry, inside);
+    const Points<float>& out = std::get<Points<float>>(inside[0]);
+    dump(f, out.get_pos()[0]); dump(f, out.get_pos()[1]);
+  }
   fclose(f);
   printf("test_find_vels: wrote %s\n", argv[1]);
   return 0;

@@ -1,5 +1,6 @@
 """Generate tests/golden/ref_golden_reflect.npz from the UNMODIFIED reference build (oracle/_ref): outputs of the
-reference's own clear_inner_layer<float> (method 1, src/Reflect.h:490-768) on its own Collections.
+reference's own clear_inner_layer<float> (method 1, src/Reflect.h:490-768) and reflect_interior<float> (:174-380)
+on its own Collections.
 
     python tests/golden/make_golden_reflect.py        (in the build container: needs /root/reference)
 """
@@ -49,6 +50,16 @@ def main():
     qx = rng.uniform(-0.65, 0.65, n).astype(np.float32); qy = rng.uniform(-0.65, 0.65, n).astype(np.float32)
     x, y, _ = R.clear_inner_layer(sx, sy, sidx, qx, qy, CF, IPS, s, r)
     out.update(sq_nx=sx, sq_ny=sy, sq_idx=sidx, sq_px=qx, sq_py=qy, sq_out=np.stack([x, y]))
+    # reflect_interior: same bodies; particles inside, near and outside.  The square set is seeded with the
+    # exact-tie cases: the centre (four nodes, eight hits, normals cancel -> hits[0] fallback, :305-317), points
+    # on the axes and diagonals (two-sided ties), a point exactly on a node and one exactly on a panel.
+    x, y = R.reflect_interior(cx, cy, cidx, px, py, s, r)
+    out["circ_reflect"] = np.stack([x, y])
+    special = np.array([[0.0, 0.0], [0.0, 0.25], [0.25, 0.0], [-0.125, 0.0], [0.25, 0.25], [-0.3, 0.3], [0.45, 0.45],
+                        [0.5, 0.5], [0.5, 0.0125], [0.4875, -0.5], [0.0, -0.4], [0.49, 0.0]], np.float32)
+    rx = np.concatenate([special[:, 0], qx[special.shape[0]:]]); ry = np.concatenate([special[:, 1], qy[special.shape[0]:]])
+    x, y = R.reflect_interior(sx, sy, sidx, rx, ry, s, r)
+    out.update(sq_rx=rx, sq_ry=ry, sq_reflect=np.stack([x, y]))
     path = os.path.join(ROOT, "tests", "golden", "ref_golden_reflect.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -102,3 +102,8 @@ def test_find_vels_cpp_vs_oracle(tmp_path, port):
     want = port.clear_inner_layer(nx, ny, idx, qx, qy, np.float32(0.5) / np.sqrt(np.float32(2.0) * np.float32(3.14159265)), 0.02191)
     assert want[2] > 10
     assert np.hypot(ox - want[0], oy - want[1]).max() < 1e-5
+    # reflect_interior through the mirror (ReflectB200.h -> o2d_reflect_interior)
+    qx, qy, ox, oy = arrs[35:39]
+    want = port.reflect_interior(nx, ny, idx, qx, qy)
+    assert want[2] > 10
+    assert np.hypot(ox - want[0], oy - want[1]).max() < 1e-5
