@@ -270,6 +270,34 @@ int o2d_reflect_interior(o2d_context* ctx, int mem,
 int o2d_points_status(o2d_context* ctx, int mem, int n, const float* x, const float* y, const float* s,
                       float* total_circ, float* impulse_x, float* impulse_y, float* max_str);
 
+/* ---- .vtu output of a particle collection ----------------------------------------------------- */
+
+/*
+ * The .vtu file image Points<S>::write_vtk produces (reference src/Points.h:556-740; VtkXmlWriter::unpackArray /
+ * writeDataArray src/VtkXmlWriter.h:71-106, base64 through reference lib/cppcodec/base64_rfc4648.hpp), byte for
+ * byte: XML skeleton as tinyxml2 prints it, every DataArray as ' ' + base64(UInt32 length of the encoded text) +
+ * base64(data) + ' '.  The arrays are encoded on the GPU straight from the SoA arrays (the (x,y,0) interleave and
+ * the connectivity/offsets/types arrays never exist in memory); only the finished text crosses PCIe.
+ *   x,y,u,v  positions and velocities (n each; `mem` says where they live)
+ *   s,r      circulation and radius, both NULL for inert field points (src/Points.h:561-568)
+ *   w,e      vorticity / shear rate or NULL (ElementBase::has_vort / has_shear, src/ElementBase.h:63,96)
+ *   time     the FieldData TimeValue
+ *   out,cap  HOST buffer receiving the image (always host memory: it is a file); *written = its size, also
+ *            set when cap is too small (then O2D_ERR_INVALID is returned and nothing is written)
+ * o2d_vtu_points_size gives the exact size beforehand.  n must be > 0 (the reference asserts it) and < 2^28
+ * (the format's UInt32 array header).  o2d_write_vtu_points writes the image to `path` through a pinned
+ * buffer owned by the context; the caller composes the reference's file name ("part_%02d_%05d.vtu" /
+ * "fldpt_...", src/Points.h:570-573).
+ */
+int o2d_vtu_points_size(int n, int has_s, int has_r, int has_w, int has_e, size_t* bytes);
+int o2d_vtu_points(o2d_context* ctx, int mem, int n, const float* x, const float* y,
+                   const float* s, const float* r, const float* w, const float* e,
+                   const float* u, const float* v, double time,
+                   char* out, size_t cap, size_t* written);
+int o2d_write_vtu_points(o2d_context* ctx, int mem, const char* path, int n, const float* x, const float* y,
+                         const float* s, const float* r, const float* w, const float* e,
+                         const float* u, const float* v, double time);
+
 /* ---- the reference's existing plugin seam ---------------------------------------------- */
 
 /*

@@ -88,6 +88,9 @@ def load_library() -> C.CDLL:
     lib.o2d_points_on_panels_sharded.argtypes = [vp, i, i, vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp]
     lib.o2d_points_status.argtypes = [vp, i, i, vp, vp, vp] + [C.POINTER(C.c_float)] * 4
     lib.o2d_add_rot_strengths.argtypes = [vp, i, i, i, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, vp, vp]
+    lib.o2d_vtu_points_size.argtypes = [i, i, i, i, i, C.POINTER(C.c_size_t)]
+    lib.o2d_vtu_points.argtypes = [vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp, d, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.o2d_write_vtu_points.argtypes = [vp, i, C.c_char_p, i, vp, vp, vp, vp, vp, vp, vp, vp, d]
     lib.external_vel_solver_f_.restype = C.c_float
     lib.external_vel_solver_f_.argtypes = [C.POINTER(i), vp, vp, vp, vp, C.POINTER(i), vp, vp, vp, vp]
     lib.external_vel_solver_tr_f_.restype = C.c_float
@@ -108,6 +111,15 @@ def load_library() -> C.CDLL:
 
 def flops_per_pair(kind: int, core: str = "rm", results: int = VELONLY, blob_targets: bool = True) -> int:
     return int(load_library().o2d_flops_per_pair(kind, CORE_ID[core], results, int(blob_targets)))
+
+
+def vtu_points_size(n: int, has_s=True, has_r=True, has_w=False, has_e=False) -> int:
+    lib = load_library()
+    out = C.c_size_t(0)
+    rc = lib.o2d_vtu_points_size(int(n), int(bool(has_s)), int(bool(has_r)), int(bool(has_w)), int(bool(has_e)), C.byref(out))
+    if rc != OK:
+        raise O2DError(rc, lib.o2d_last_error().decode())
+    return int(out.value)
 
 
 def _ptr(a):
@@ -281,6 +293,21 @@ class Context:
         self._check(self.lib.o2d_points_status(self._h, int(mem), int(n), _ptr(x), _ptr(y), _ptr(s),
                                                *[C.byref(o) for o in out]))
         return tuple(o.value for o in out)
+
+    def vtu_points(self, mem, n, x, y, s, r, u, v, time, w=None, e=None, cap=None) -> bytes:
+        """The .vtu file image of Points::write_vtk as bytes (o2d_vtu_points)."""
+        need = vtu_points_size(n, s is not None, r is not None, w is not None, e is not None)
+        cap = need if cap is None else int(cap)
+        buf = np.empty(max(cap, 1), dtype=np.uint8)
+        wrote = C.c_size_t(0)
+        self._check(self.lib.o2d_vtu_points(self._h, int(mem), int(n), _ptr(x), _ptr(y), _ptr(s), _ptr(r), _ptr(w), _ptr(e),
+                                            _ptr(u), _ptr(v), float(time), _ptr(buf), cap, C.byref(wrote)))
+        assert wrote.value == need
+        return buf[:wrote.value].tobytes()
+
+    def write_vtu_points(self, mem, path, n, x, y, s, r, u, v, time, w=None, e=None):
+        self._check(self.lib.o2d_write_vtu_points(self._h, int(mem), str(path).encode(), int(n), _ptr(x), _ptr(y), _ptr(s),
+                                                  _ptr(r), _ptr(w), _ptr(e), _ptr(u), _ptr(v), float(time)))
 
     def add_rot_strengths(self, mem, np_, nnodes, ux, uy, idx, area, center, rotvel, vs, ss):
         self._check(self.lib.o2d_add_rot_strengths(self._h, int(mem), int(np_), int(nnodes), _ptr(ux), _ptr(uy), _ptr(idx),

@@ -130,8 +130,9 @@ extern "C" int o2d_destroy(o2d_context* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   o2d_comm_destroy(c);
-  for (DevBuf* b : {&c->packed, &c->packed_all, &c->partial, &c->panel_packed, &c->hsrc, &c->htgt, &c->hout, &c->hidx, &c->hpan, &c->adv, &c->coef, &c->counter})
+  for (DevBuf* b : {&c->packed, &c->packed_all, &c->partial, &c->panel_packed, &c->hsrc, &c->htgt, &c->hout, &c->hidx, &c->hpan, &c->adv, &c->coef, &c->counter, &c->vtu})
     b->release();
+  if (c->vtu_host) cudaFreeHost(c->vtu_host);
   for (auto& pr : c->ev_pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (auto& pr : c->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   cudaEventDestroy(c->ev_gather);

@@ -1,5 +1,5 @@
 // o2d_context.h -- private: the context object and host-side helpers shared by the translation units
-// that implement the C ABI (o2d_api.cu, o2d_substep.cu, o2d_bem.cu).  Not installed.
+// that implement the C ABI (o2d_api.cu, o2d_substep.cu, o2d_bem.cu, o2d_reflect.cu, o2d_status.cu, o2d_vtu.cu).  Not installed.
 #pragma once
 #include "../../include/omega2d_b200.h"
 #include "o2d_internal.h"
@@ -53,6 +53,9 @@ struct o2d_context {
   DevBuf adv;                            // o2d_advect: intermediate Runge-Kutta stages
   DevBuf counter;                        // small device-side counters
   DevBuf coef;                           // o2d_panels_on_panels_coeff: device copy of the matrix block
+  DevBuf vtu;                            // o2d_vtu_points: base64 staging
+  void* vtu_host = nullptr;              // o2d_write_vtu_points: pinned file image
+  size_t vtu_host_cap = 0;
   // comm
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;

@@ -23,6 +23,8 @@ if [ -d "$REF/src" ]; then
 #include "ConvectionB200.h"
 #include "CoefficientsB200.h"
 #include "ReflectB200.h"
+#include "VtkB200.h"
+std::string vtk(const Points<float>& p) { return write_vtk_points(p, 0, 1, 0.5); }
 void clear(std::vector<Collection>& b, std::vector<Collection>& v) { clear_inner_layer<float>(1, b, v, 0.2f, 0.02f); }
 void reflect(std::vector<Collection>& b, std::vector<Collection>& v) { reflect_interior<float>(b, v); }
 Vector<float> coeff_block(Collection& a, Collection& b) { return std::visit(CoefficientVisitor<float>(), a, b); }

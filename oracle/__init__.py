@@ -268,6 +268,19 @@ class Port:
         out = [C.c_float() for _ in range(4)]
         self.lib.o2d_oracle_points_status(int(x.size), _f(x), _f(y), _f(s), *[C.byref(o) for o in out])
         return tuple(o.value for o in out)
+    def vtu_points(self, time, x, y, s, r, u, v, w=None, e=None) -> bytes:
+        """Restated Points::write_vtk: the bytes of the .vtu file."""
+        x, y, u, v = map(_f32, (x, y, u, v))
+        s, r, w, e = (None if a is None else _f32(a) for a in (s, r, w, e))
+        self.lib.o2d_oracle_vtu_points_bound.restype = C.c_size_t
+        cap = self.lib.o2d_oracle_vtu_points_bound(int(x.size))
+        buf = C.create_string_buffer(cap)
+        f = self.lib.o2d_oracle_vtu_points
+        f.restype = C.c_longlong
+        f.argtypes = [C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_double, C.c_char_p]
+        nb = f(int(x.size), _f(x), _f(y), _f(s), _f(r), _f(w), _f(e), _f(u), _f(v), float(time), buf)
+        assert nb > 0
+        return buf.raw[:nb]
     def add_rot_strengths(self, ux, uy, idx, area, center, rotvel, vs, ss):
         ux, uy, area = map(_f32, (ux, uy, area)); idx = np.ascontiguousarray(idx, dtype=np.uint32)
         vs, ss = np.array(vs, np.float32), np.array(ss, np.float32)
@@ -448,15 +461,16 @@ class Ref:
         rc = f(int(idx.size // 2), int(nx.size), _f(nx), _f(ny), _u(idx), int(x.size), _f(x), _f(y), _f(s), _f(r))
         assert rc == 0
         return x, y
-    def write_vtk_points(self, directory, index, frameno, time, x, y, s, r, u, v, w=None):
+    def write_vtk_points(self, directory, index, frameno, time, x, y, s, r, u, v, w=None, e=None):
         """The reference's own Points::write_vtk.  Returns the bytes of the .vtu file it wrote and its name."""
         x, y, u, v = map(_f32, (x, y, u, v))
         s = None if s is None else _f32(s); r = None if r is None else _f32(r); w = None if w is None else _f32(w)
+        e = None if e is None else _f32(e)
         f = self.lib.o2dref_write_vtk_points
-        f.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_char_p, C.c_int]
+        f.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_char_p, C.c_int]
         buf = C.create_string_buffer(256)
         rc = f(str(directory).encode(), int(index), int(frameno), float(time), int(x.size), _f(x), _f(y), _f(s), _f(r),
-               _f(u), _f(v), _f(w), buf, 256)
+               _f(u), _f(v), _f(w), _f(e), buf, 256)
         assert rc == 0, rc
         name = buf.value.decode()
         with open(os.path.join(str(directory), name), "rb") as fh:

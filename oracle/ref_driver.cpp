@@ -484,16 +484,18 @@ int o2dref_reflect_interior(int np, int nnodes, const float* nx, const float* ny
 
 // reference Points<float>::write_vtk (src/Points.h:556-740; VtkXmlWriter.h, cppcodec base64, tinyxml2 printer) on
 // the reference's own Points: blobs (s != NULL: circulation + radius arrays) or inert field points; w != NULL
-// also engages the vorticity array.  The file is written into `dir` (the reference writes into the current
+// also engages the vorticity array, e != NULL the shear-rate array.  The file is written into `dir` (the reference writes into the current
 // directory); its name (e.g. part_00_00007.vtu) is returned in fname.
 int o2dref_write_vtk_points(const char* dir, int index, int frameno, double time,
                             int n, const float* x, const float* y, const float* s, const float* r,
-                            const float* u, const float* v, const float* w, char* fname, int fname_len) {
+                            const float* u, const float* v, const float* w, const float* e,
+                            char* fname, int fname_len) {
   StdoutMute mute;
   Points<float> p = make_points(n, x, y, s, r);
   auto& pu = p.get_vel();
   for (int i = 0; i < n; ++i) { pu[0][i] = u[i]; pu[1][i] = v[i]; }
   if (w) { auto& pw = p.get_vort(); for (int i = 0; i < n; ++i) pw[i] = w[i]; }
+  if (e) { auto& pe = p.get_shear(); for (int i = 0; i < n; ++i) pe[i] = e[i]; }
   char cwd[4096];
   if (!getcwd(cwd, sizeof(cwd))) return -1;
   if (chdir(dir) != 0) return -2;

@@ -5,6 +5,7 @@
 #include "ConvectionB200.h"
 #include "CoefficientsB200.h"
 #include "ReflectB200.h"
+#include "VtkB200.h"
 
 #include <cstdio>
 #include <cstdint>
@@ -119,6 +120,15 @@ int main(int argc, char** argv) {
     reflect_interior<float>(bdry, inside);
     const Points<float>& out = std::get<Points<float>>(inside[0]);
     dump(f, out.get_pos()[0]); dump(f, out.get_pos()[1]);
+  }
+  // .vtu output of the particles (with vorticity) and of the tracers, next to the dump file
+  {
+    std::string dir(argv[1]);
+    const size_t slash = dir.find_last_of('/');
+    dir = slash == std::string::npos ? std::string(".") : dir.substr(0, slash);
+    const std::string a = write_vtk_points(std::get<Points<float>>(vort[0]), 0, 7, 0.25, dir);
+    const std::string b = write_vtk_points(std::get<Points<float>>(fldpt[0]), 1, 7, 0.25, dir);
+    if (a != "part_00_00007.vtu" || b != "fldpt_01_00007.vtu") { fprintf(stderr, "bad vtu names %s %s\n", a.c_str(), b.c_str()); return 4; }
   }
   fclose(f);
   printf("test_find_vels: wrote %s\n", argv[1]);

@@ -107,3 +107,6 @@ def test_find_vels_cpp_vs_oracle(tmp_path, port):
     want = port.reflect_interior(nx, ny, idx, qx, qy)
     assert want[2] > 10
     assert np.hypot(ox - want[0], oy - want[1]).max() < 1e-5
+    # .vtu files through the mirror (VtkB200.h -> o2d_write_vtu_points): byte-identical to the restated writer
+    assert (tmp_path / "part_00_00007.vtu").read_bytes() == port.vtu_points(0.25, vx, vy, vs_, vr, wu, wv, w=ww)
+    assert (tmp_path / "fldpt_01_00007.vtu").read_bytes() == port.vtu_points(0.25, fx, fy, None, None, np.zeros_like(fx), np.zeros_like(fx), w=fw)   # find_vort zeroed the velocities
