@@ -294,10 +294,17 @@ class Context:
                                                *[C.byref(o) for o in out]))
         return tuple(o.value for o in out)
 
-    def vtu_points(self, mem, n, x, y, s, r, u, v, time, w=None, e=None, cap=None) -> bytes:
-        """The .vtu file image of Points::write_vtk as bytes (o2d_vtu_points)."""
+    def vtu_points(self, mem, n, x, y, s, r, u, v, time, w=None, e=None, cap=None, out=None):
+        """The .vtu file image of Points::write_vtk as bytes (o2d_vtu_points).  With `out` (a host uint8 buffer, e.g.
+        pinned) the image is written there and its size is returned instead."""
         need = vtu_points_size(n, s is not None, r is not None, w is not None, e is not None)
         cap = need if cap is None else int(cap)
+        if out is not None:
+            wrote = C.c_size_t(0)
+            self._check(self.lib.o2d_vtu_points(self._h, int(mem), int(n), _ptr(x), _ptr(y), _ptr(s), _ptr(r), _ptr(w), _ptr(e),
+                                                _ptr(u), _ptr(v), float(time), _ptr(out), int(out.numel() if hasattr(out, "numel") else out.size),
+                                                C.byref(wrote)))
+            return wrote.value
         buf = np.empty(max(cap, 1), dtype=np.uint8)
         wrote = C.c_size_t(0)
         self._check(self.lib.o2d_vtu_points(self._h, int(mem), int(n), _ptr(x), _ptr(y), _ptr(s), _ptr(r), _ptr(w), _ptr(e),

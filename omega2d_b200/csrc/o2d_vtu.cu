@@ -296,9 +296,12 @@ extern "C" int o2d_vtu_points(o2d_context* c, int mem, int n, const float* x, co
     nblocks += (unsigned int)((groups + kVtuThreads - 1) / kVtuThreads);
     off += align256(b64_len(pc[k].nbytes) + 16);
   }
-  vtu_encode_kernel<<<nblocks, kVtuThreads, 0, c->stream>>>(a);
-  CU(cudaGetLastError());
-  c->launches += 1;
+  {
+    PairTimer timer(c);
+    vtu_encode_kernel<<<nblocks, kVtuThreads, 0, c->stream>>>(a);
+    CU(cudaGetLastError());
+    c->launches += 1;
+  }
 
   // ---- assemble the image: skeleton text from the host, payloads from the device -----------------------------
   size_t pos = 0;

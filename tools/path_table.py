@@ -228,6 +228,47 @@ err = float(max(np.abs(gx - want[0]).max(), np.abs(gy - want[1]).max()))
 add("clear_inner_layer (push)", "`clear_inner_panp2` Reflect.h:490-733", float(npc) * n, "panel-point tests", ms,
     float(npc) * csub.size, sec, err, note=f"first sweep counted; error = max |dx| (absolute); CPU sample {csub.size} particles")
 
+# ---- reflect_interior -------------------------------------------------------------------------------------------------------
+def run():
+    state["x"], state["y"] = T(qx), T(qy)
+    ctx.reflect_interior(o2d.MEM_DEVICE, npc, cx.size, dc[0], dc[1], dcidx, dn[0], dn[1], n, state["x"], state["y"])
+
+
+ms = gpu_ms(run, reps=2)
+sec, want = cpu_s(lambda: oracle.ref("rm").reflect_interior(cx, cy, cidx, qx[csub], qy[csub], s[csub], r[csub]))
+gx, gy = state["x"].cpu().numpy()[csub], state["y"].cpu().numpy()[csub]
+err = float(max(np.abs(gx - want[0]).max(), np.abs(gy - want[1]).max()))
+add("reflect_interior", "`reflect_panp2` Reflect.h:174-350", float(npc) * n, "panel-point tests", ms,
+    float(npc) * csub.size, sec, err, note=f"error = max |dx| (absolute); CPU sample {csub.size} particles")
+
+# ---- .vtu output ------------------------------------------------------------------------------------------------------------
+import tempfile
+u_w = np.random.default_rng(3).standard_normal((2, n)).astype(np.float32)
+du = [T(a) for a in u_w]
+vtu_bytes = o2d.vtu_points_size(n)
+tmpd = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+vpath = os.path.join(tmpd, "part_00_00001.vtu")
+kms = gpu_ms(lambda: ctx.write_vtu_points(o2d.MEM_DEVICE, vpath, n, d[0], d[1], d[2], d[3], du[0], du[1], 0.5))
+t0 = time.perf_counter()
+for _ in range(3):
+    ctx.write_vtu_points(o2d.MEM_DEVICE, vpath, n, d[0], d[1], d[2], d[3], du[0], du[1], 0.5)
+e2e_ms = (time.perf_counter() - t0) / 3 * 1e3
+got = open(vpath, "rb").read()
+pinned = torch.empty(vtu_bytes, dtype=torch.uint8).pin_memory()
+ctx.vtu_points(o2d.MEM_DEVICE, n, d[0], d[1], d[2], d[3], du[0], du[1], 0.5, out=pinned)
+t0 = time.perf_counter()
+for _ in range(5):
+    ctx.vtu_points(o2d.MEM_DEVICE, n, d[0], d[1], d[2], d[3], du[0], du[1], 0.5, out=pinned)
+img_ms = (time.perf_counter() - t0) / 5 * 1e3
+assert pinned.numpy().tobytes() == got
+t0 = time.perf_counter(); want, _ = oracle.ref("rm").write_vtk_points(tmpd, 0, 2, 0.5, x, y, s, r, u_w[0], u_w[1]); sec = time.perf_counter() - t0
+nbad = 0 if got == want else 1 + sum(a != b for a, b in zip(got, want))
+add("write_vtk (.vtu image of the particles)", "`Points::write_vtk` Points.h:556-740, VtkXmlWriter.h:71-106", float(vtu_bytes), "file bytes", kms,
+    float(vtu_bytes), sec, float(nbad), note=f"GPU ms = the encode kernel alone ({(24 * n + vtu_bytes) / (kms * 1e-3) / 1e9:.0f} GB/s of HBM traffic); "
+    f"o2d_vtu_points, finished image in pinned host memory (kernel + skeleton + D2H): {img_ms:.2f} ms = {vtu_bytes / (img_ms * 1e-3) / 1e9:.1f} GB/s; "
+    f"o2d_write_vtu_points, the same plus fwrite of the image to tmpfs: {e2e_ms:.1f} ms ({sec * 1e3 / e2e_ms:.0f}x the reference's writer, whose time "
+    f"also includes its file write); error column = number of differing bytes (0 = identical file)")
+
 # ---- status reductions, zero/finalize ----------------------------------------------------------------------------------------
 ms = wall_ms(lambda: ctx.points_status(o2d.MEM_DEVICE, n, d[0], d[1], d[2]), reps=5)
 t0 = time.perf_counter(); want = oracle.port().points_status(x, y, s); sec = time.perf_counter() - t0
@@ -237,7 +278,7 @@ add("points_status (circulation, impulse, max strength)", "ElementBase.h:362-394
     float(n), sec, err, note="GPU time includes the 4-float result read-back; CPU = C restatement, one thread; the reference sums serially in float32, the GPU in float64 (fixed order)")
 
 hdr = [
-    f"# Every kernel of the path at full size: B200 vs the reference's CPU implementation (round 1, session 5)",
+    f"# Every kernel of the path at full size: B200 vs the reference's CPU implementation (round 1)",
     "",
     f"`python tools/path_table.py --n {n} --panels {args.panels}` on one B200 ({info['sm_count']} SMs, {info['sm_clock_mhz']} MHz); "
     f"device-resident inputs, time = the pair kernel's own CUDA events on the launching stream (library timers), mean of 3 launches "
