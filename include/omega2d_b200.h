@@ -307,8 +307,9 @@ int o2d_write_vtu_points(o2d_context* ctx, int mem, const char* path, int n, con
  * interface2dvorttr.cpp:177-183).  Same Fortran-style signature (counts by pointer, note
  * ss BEFORE sr), same semantics: velocities are accumulated into tu,tv, the return value is
  * the flop count the caller turns into its GFlop/s print (negative on failure).  They use a
- * lazily created process-wide context on device $O2D_DEVICE (default 0) and the core set by
- * o2d_set_default_core / $O2D_CORE (rm|exp|wl|v2|v3; default v2 like the reference).
+ * lazily created process-wide context on device $O2D_DEVICE (default 0) -- or, with $O2D_DEVICES=N|all, a
+ * process-wide o2d_group over N (all visible) GPUs -- and the core set by o2d_set_default_core / $O2D_CORE
+ * (rm|exp|wl|v2|v3; default v2 like the reference).
  */
 float external_vel_solver_f_(int* ns, const float* sx, const float* sy, const float* ss, const float* sr,
                              int* nt, const float* tx, const float* ty, float* tu, float* tv);
@@ -364,6 +365,44 @@ int o2d_points_on_panels_sharded(o2d_context* ctx, int mem,
                                  int ns_local, const float* sx, const float* sy, const float* ss,
                                  int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
                                  const float* area, float* pu, float* pv);
+
+/* ---- all GPUs of the box from ONE process ------------------------------------------------------- */
+
+/*
+ * Omega2D is a single-process OpenMP program whose influence loops are "omp parallel for" over the targets
+ * (reference src/Influence.h:198,348).  A group applies the same decomposition to devices: HOST arrays in, the
+ * target collection cut into one contiguous block per GPU (multiples of 1024), the whole source collection
+ * uploaded to every GPU over its own PCIe link, one host thread per device driving the single-device entry
+ * point above on its block, results written to disjoint slices of the caller's arrays.  Argument meaning and
+ * accumulate / overwrite semantics are those of the single-device call of the same name.  Small problems
+ * (fewer than `pairs_per_device` pair evaluations per device, default 2e9; a panel pair counts as five) use
+ * fewer devices, down to one.  o2d_group_points_on_panels cuts the SOURCES instead (targets are the few
+ * panels) and adds the devices' per-panel sums on the host in fixed order.
+ *   devices == NULL: devices 0..ndev-1;  ndev <= 0: every visible device.
+ */
+typedef struct o2d_group o2d_group;
+int o2d_group_create(o2d_group** group, int ndev, const int* devices);
+int o2d_group_destroy(o2d_group* group);
+int o2d_group_size(const o2d_group* group);
+o2d_context* o2d_group_context(o2d_group* group, int slot);   /* the slot's context, e.g. for the other calls */
+int o2d_group_set_min_pairs(o2d_group* group, long long pairs_per_device);
+int o2d_group_points_on_points(o2d_group* group, int core, int results,
+                               int ns, const float* sx, const float* sy, const float* ss, const float* sr,
+                               int nt, const float* tx, const float* ty, const float* tr,
+                               float* tu, float* tv, float* tq,
+                               float* tux, float* tvx, float* tuy, float* tvy);
+int o2d_group_find_vels(o2d_group* group, int core, int results,
+                        int nv, const float* vx, const float* vy, const float* vs, const float* vr,
+                        int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                        const float* pvs, const float* pss,
+                        int nt, const float* tx, const float* ty, const float* tr,
+                        float* tu, float* tv, float* tq, double fsx, double fsy);
+int o2d_group_panels_on_points(o2d_group* group, int np, int nnodes, const float* nx, const float* ny,
+                               const uint32_t* idx, const float* vs, const float* ss,
+                               int nt, const float* tx, const float* ty, float* tu, float* tv);
+int o2d_group_points_on_panels(o2d_group* group, int ns, const float* sx, const float* sy, const float* ss,
+                               int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                               const float* area, float* pu, float* pv);
 
 /* ---- measurement hooks (used by bench.py; no effect on results) ------------------------- */
 

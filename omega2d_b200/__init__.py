@@ -91,6 +91,16 @@ def load_library() -> C.CDLL:
     lib.o2d_vtu_points_size.argtypes = [i, i, i, i, i, C.POINTER(C.c_size_t)]
     lib.o2d_vtu_points.argtypes = [vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp, d, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.o2d_write_vtu_points.argtypes = [vp, i, C.c_char_p, i, vp, vp, vp, vp, vp, vp, vp, vp, d]
+    lib.o2d_group_create.argtypes = [C.POINTER(vp), i, C.POINTER(i)]
+    lib.o2d_group_destroy.argtypes = [vp]
+    lib.o2d_group_size.argtypes = [vp]
+    lib.o2d_group_context.argtypes = [vp, i]
+    lib.o2d_group_context.restype = vp
+    lib.o2d_group_set_min_pairs.argtypes = [vp, C.c_longlong]
+    lib.o2d_group_points_on_points.argtypes = [vp, i, i, i, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.o2d_group_find_vels.argtypes = [vp, i, i, i, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, vp, d, d]
+    lib.o2d_group_panels_on_points.argtypes = [vp, i, i, vp, vp, vp, vp, vp, i, vp, vp, vp, vp]
+    lib.o2d_group_points_on_panels.argtypes = [vp, i, vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp]
     lib.external_vel_solver_f_.restype = C.c_float
     lib.external_vel_solver_f_.argtypes = [C.POINTER(i), vp, vp, vp, vp, C.POINTER(i), vp, vp, vp, vp]
     lib.external_vel_solver_tr_f_.restype = C.c_float
@@ -111,6 +121,66 @@ def load_library() -> C.CDLL:
 
 def flops_per_pair(kind: int, core: str = "rm", results: int = VELONLY, blob_targets: bool = True) -> int:
     return int(load_library().o2d_flops_per_pair(kind, CORE_ID[core], results, int(blob_targets)))
+
+
+class Group:
+    """Several GPUs driven from this one process (o2d_group_*): host arrays in, targets cut into one block per device."""
+
+    def __init__(self, devices=None, min_pairs=None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        if devices is None:
+            rc = self.lib.o2d_group_create(C.byref(h), 0, None)
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self.lib.o2d_group_create(C.byref(h), len(devices), arr)
+        if rc != OK:
+            raise O2DError(rc, self.lib.o2d_last_error().decode())
+        self._h = h
+        if min_pairs is not None:
+            self._check(self.lib.o2d_group_set_min_pairs(self._h, int(min_pairs)))
+
+    def _check(self, rc):
+        if rc != OK:
+            raise O2DError(rc, self.lib.o2d_last_error().decode())
+
+    @property
+    def size(self):
+        return int(self.lib.o2d_group_size(self._h))
+
+    def close(self):
+        if self._h:
+            self.lib.o2d_group_destroy(self._h)
+            self._h = None
+
+    def points_on_points(self, core, results, sx, sy, ss, sr, tx, ty, tr, tu, tv, tq=None, tux=None, tvx=None, tuy=None, tvy=None):
+        core = CORE_ID[core] if isinstance(core, str) else int(core)
+        self._check(self.lib.o2d_group_points_on_points(self._h, core, int(results), int(sx.size), _ptr(sx), _ptr(sy), _ptr(ss), _ptr(sr),
+                                                        int(tx.size), _ptr(tx), _ptr(ty), _ptr(tr), _ptr(tu), _ptr(tv), _ptr(tq),
+                                                        _ptr(tux), _ptr(tvx), _ptr(tuy), _ptr(tvy)))
+
+    def find_vels(self, core, results, vort, panels, tx, ty, tr, tu, tv, tq=None, fs=(0.0, 0.0)):
+        core = CORE_ID[core] if isinstance(core, str) else int(core)
+        vx, vy, vs, vr = vort
+        if panels is not None:
+            nx, ny, idx, pvs, pss = panels
+            npan, nn = pvs.size, nx.size
+        else:
+            nx = ny = idx = pvs = pss = None
+            npan = nn = 0
+        self._check(self.lib.o2d_group_find_vels(self._h, core, int(results), int(vx.size), _ptr(vx), _ptr(vy), _ptr(vs), _ptr(vr),
+                                                 int(npan), int(nn), _ptr(nx), _ptr(ny), _ptr(idx), _ptr(pvs), _ptr(pss),
+                                                 int(tx.size), _ptr(tx), _ptr(ty), _ptr(tr), _ptr(tu), _ptr(tv), _ptr(tq),
+                                                 float(fs[0]), float(fs[1])))
+
+    def panels_on_points(self, panels, tx, ty, tu, tv):
+        nx, ny, idx, pvs, pss = panels
+        self._check(self.lib.o2d_group_panels_on_points(self._h, int(pvs.size), int(nx.size), _ptr(nx), _ptr(ny), _ptr(idx), _ptr(pvs),
+                                                        _ptr(pss), int(tx.size), _ptr(tx), _ptr(ty), _ptr(tu), _ptr(tv)))
+
+    def points_on_panels(self, sx, sy, ss, nx, ny, idx, area, pu, pv):
+        self._check(self.lib.o2d_group_points_on_panels(self._h, int(sx.size), _ptr(sx), _ptr(sy), _ptr(ss), int(area.size), int(nx.size),
+                                                        _ptr(nx), _ptr(ny), _ptr(idx), _ptr(area), _ptr(pu), _ptr(pv)))
 
 
 def vtu_points_size(n: int, has_s=True, has_r=True, has_w=False, has_e=False) -> int:

@@ -617,6 +617,7 @@ extern "C" int o2d_finalize_vels(o2d_context* c, int mem, int n, float* u, float
 // ---- legacy plugin seam ------------------------------------------------------------------------------------------
 static std::mutex g_legacy_mu;
 static o2d_context* g_legacy_ctx = nullptr;
+static o2d_group* g_legacy_group = nullptr;
 static int g_default_core = -1;
 
 static int default_core_locked() {
@@ -645,17 +646,26 @@ static float legacy_solve(int* ns, const float* sx, const float* sy, const float
                           int* nt, const float* tx, const float* ty, const float* tr, float* tu, float* tv) {
   std::lock_guard<std::mutex> lk(g_legacy_mu);
   if (!ns || !nt) { fail(O2D_ERR_INVALID, "NULL count"); return -1.0f; }
-  if (!g_legacy_ctx) {
-    int dev = 0;
-    if (const char* e = getenv("O2D_DEVICE")) dev = atoi(e);
-    if (o2d_create(&g_legacy_ctx, dev) != O2D_OK) {
+  if (!g_legacy_ctx && !g_legacy_group) {
+    int rc;
+    if (const char* e = getenv("O2D_DEVICES")) {        // several GPUs from this one process (o2d_group.cu)
+      rc = o2d_group_create(&g_legacy_group, strcasecmp(e, "all") == 0 ? 0 : atoi(e), nullptr);
+    } else {
+      int dev = 0;
+      if (const char* e1 = getenv("O2D_DEVICE")) dev = atoi(e1);
+      rc = o2d_create(&g_legacy_ctx, dev);
+    }
+    if (rc != O2D_OK) {
       fprintf(stderr, "omega2d_b200: %s\n", o2d_last_error());
       return -1.0f;
     }
   }
   const int core = default_core_locked();
-  int rc = o2d_points_on_points(g_legacy_ctx, core, O2D_VELONLY, O2D_MEM_HOST, *ns, sx, sy, ss, sr, *nt, tx, ty, tr,
-                                tu, tv, nullptr, nullptr, nullptr, nullptr, nullptr);
+  int rc = g_legacy_group
+    ? o2d_group_points_on_points(g_legacy_group, core, O2D_VELONLY, *ns, sx, sy, ss, sr, *nt, tx, ty, tr,
+                                 tu, tv, nullptr, nullptr, nullptr, nullptr, nullptr)
+    : o2d_points_on_points(g_legacy_ctx, core, O2D_VELONLY, O2D_MEM_HOST, *ns, sx, sy, ss, sr, *nt, tx, ty, tr,
+                           tu, tv, nullptr, nullptr, nullptr, nullptr, nullptr);
   if (rc != O2D_OK) {
     fprintf(stderr, "omega2d_b200: %s\n", o2d_last_error());
     return -1.0f;

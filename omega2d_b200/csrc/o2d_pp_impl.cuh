@@ -258,12 +258,9 @@ template <int CORE, int RES, bool FINE>
 static cudaError_t launch_one(const PPArgs& a, int nchunks, cudaStream_t st) {
   using C = PPConfig<CORE, RES, FINE>;
   auto kern = C::kernel();
-  static bool configured = false;   // one context per thread, but the attribute is per function
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  // two 16 KiB stages + barriers: under the 48 KiB a kernel gets without opting in, so there is no per-device
+  // function attribute to set (a process may drive several devices, o2d_group.cu)
+  static_assert(C::SMEM <= 48 * 1024, "dynamic shared memory above the default limit needs cudaFuncSetAttribute per device");
   const int nb = (a.nt + C::THREADS * C::R - 1) / (C::THREADS * C::R);
   dim3 grid(nb, nchunks, 1);
   kern<<<grid, C::THREADS, C::SMEM, st>>>(a);
@@ -274,7 +271,6 @@ template <int CORE, int RES, bool FINE>
 static int occupancy_one() {
   using C = PPConfig<CORE, RES, FINE>;
   auto kern = C::kernel();
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
   int nb = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, C::THREADS, C::SMEM) != cudaSuccess) return 1;
   return nb > 0 ? nb : 1;

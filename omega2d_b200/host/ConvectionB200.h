@@ -32,7 +32,7 @@ bool fused_find_vels(const std::array<double,Dimensions>& _fs, std::vector<Colle
   // finalize_vels also scales whichever of w/e the collection carries; keep the one not computed here
   // consistent with the unfused sequence (zeroed, then scaled: stays zero)
   targ.zero_vels();
-  check(o2d_find_vels(device(), selected_core(), (int)_results, O2D_MEM_HOST,
+  check(o2d_group_find_vels(group(), selected_core(), (int)_results,
                       (int)src.get_n(), sx[0].data(), sx[1].data(), src.get_str().data(), src.get_rad().data(),
                       pan ? (int)pan->get_npanels() : 0, pan ? (int)pan->get_n() : 0,
                       pan ? pan->get_pos()[0].data() : nullptr, pan ? pan->get_pos()[1].data() : nullptr,

@@ -42,20 +42,31 @@ constexpr int selected_core() {
 #endif
 }
 
-// process-wide library context, created on first use on device $O2D_DEVICE (default 0)
-inline o2d_context* device() {
-  static o2d_context* ctx = [] {
-    o2d_context* c = nullptr;
-    int dev = 0;
-    if (const char* e = std::getenv("O2D_DEVICE")) dev = std::atoi(e);
-    if (o2d_create(&c, dev) != O2D_OK) {
+// process-wide device group, created on first use: one GPU -- device $O2D_DEVICE, default 0 -- unless
+// $O2D_DEVICES=N|all asks for several; the reference is a single-process OpenMP program, so this is how it
+// reaches all GPUs of a box (include/omega2d_b200.h, "all GPUs of the box from ONE process")
+inline o2d_group* group() {
+  static o2d_group* grp = [] {
+    o2d_group* g = nullptr;
+    int rc;
+    if (const char* e = std::getenv("O2D_DEVICES")) {
+      const bool all = (e[0] == 'a' || e[0] == 'A');
+      rc = o2d_group_create(&g, all ? 0 : std::atoi(e), nullptr);
+    } else {
+      int dev = 0;
+      if (const char* e1 = std::getenv("O2D_DEVICE")) dev = std::atoi(e1);
+      rc = o2d_group_create(&g, 1, &dev);
+    }
+    if (rc != O2D_OK) {
       std::fprintf(stderr, "omega2d_b200: %s\n", o2d_last_error());
       std::abort();
     }
-    return c;
+    return g;
   }();
-  return ctx;
+  return grp;
 }
+// the group's first context: everything that is not a big influence sum runs there
+inline o2d_context* device() { return o2d_group_context(group(), 0); }
 
 inline void check(int rc, const char* what) {
   if (rc != O2D_OK) {
@@ -108,7 +119,7 @@ void points_affect_points(const Points<S>& src, Points<S>& targ, const ResultsTy
   const int core = o2d_host::selected_core();
   const double per_pair = o2d_flops_per_pair(0, core, (int)restype.get_type(), tr != nullptr);
   o2d_host::CallTimer timer("points_affect_points", (double)targ.get_n() * (2.0 + per_pair * (double)src.get_n()));
-  o2d_host::check(o2d_points_on_points(o2d_host::device(), core, (int)restype.get_type(), O2D_MEM_HOST,
+  o2d_host::check(o2d_group_points_on_points(o2d_host::group(), core, (int)restype.get_type(),
                                        (int)src.get_n(), sx[0].data(), sx[1].data(), ss.data(), sr.data(),
                                        (int)targ.get_n(), tx[0].data(), tx[1].data(), tr,
                                        tu[0].data(), tu[1].data(), tq, nullptr, nullptr, nullptr, nullptr),
@@ -127,7 +138,7 @@ void points_affect_points_grad(const Points<S>& src, Points<S>& targ, std::array
   const auto& tx = targ.get_pos();
   auto& tu = targ.get_vel();
   const S* tr = targ.is_inert() ? nullptr : targ.get_rad().data();
-  o2d_host::check(o2d_points_on_points(o2d_host::device(), o2d_host::selected_core(), O2D_VELANDGRAD, O2D_MEM_HOST,
+  o2d_host::check(o2d_group_points_on_points(o2d_host::group(), o2d_host::selected_core(), O2D_VELANDGRAD,
                                        (int)src.get_n(), sx[0].data(), sx[1].data(), src.get_str().data(), src.get_rad().data(),
                                        (int)targ.get_n(), tx[0].data(), tx[1].data(), tr, tu[0].data(), tu[1].data(), nullptr,
                                        grads[0].data(), grads[1].data(), grads[2].data(), grads[3].data()),
@@ -151,7 +162,7 @@ void panels_affect_points(const Surfaces<S>& src, Points<S>& targ, const Results
   auto& tu = targ.get_vel();
   o2d_host::CallTimer timer("panels_affect_points",
                             (double)targ.get_n() * (2.0 + (double)o2d_flops_per_pair(ss ? 2 : 1, 0, 1, 0) * (double)src.get_npanels()));
-  o2d_host::check(o2d_panels_on_points(o2d_host::device(), O2D_MEM_HOST, (int)src.get_npanels(), (int)src.get_n(),
+  o2d_host::check(o2d_group_panels_on_points(o2d_host::group(), (int)src.get_npanels(), (int)src.get_n(),
                                        sx[0].data(), sx[1].data(), si.data(), vs.data(), ss,
                                        (int)targ.get_n(), tx[0].data(), tx[1].data(), tu[0].data(), tu[1].data()),
                   "panels_affect_points");
@@ -174,7 +185,7 @@ void points_affect_panels(const Points<S>& src, Surfaces<S>& targ, const Results
   auto& tu = targ.get_vel();
   o2d_host::CallTimer timer("points_affect_panels",
                             (double)targ.get_npanels() * (11.0 + (double)o2d_flops_per_pair(1, 0, 1, 0) * (double)src.get_n()));
-  o2d_host::check(o2d_points_on_panels(o2d_host::device(), O2D_MEM_HOST, (int)src.get_n(), sx[0].data(), sx[1].data(), vs.data(),
+  o2d_host::check(o2d_group_points_on_panels(o2d_host::group(), (int)src.get_n(), sx[0].data(), sx[1].data(), vs.data(),
                                        (int)targ.get_npanels(), (int)targ.get_n(), tx[0].data(), tx[1].data(), ti.data(),
                                        ta.data(), tu[0].data(), tu[1].data()),
                   "points_affect_panels");
