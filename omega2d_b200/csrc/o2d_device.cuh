@@ -256,11 +256,19 @@ __device__ __forceinline__ void core_eval(float2 dx, float2 dy, float2 rho, floa
     // src/CoreFunc.h:290-295,312-320: K = cbrt(d2^3 + sr^6 + tr^6)^-1, bbb = -2 d2^2 K / (d2^3+..)
     d2 = fma2(dy, dy, mul2(dx, dx));
     const float2 q = UNI ? fma2(mul2(d2, d2), d2, rho) : add2(fma2(mul2(d2, d2), d2, tau), rho);
-    // q^(-1/3) = 2^(-lg2(q)/3), then one Newton step  k <- k + k (1 - q k^3)/3  on the FMA pipe
+    // q^(-1/3) = 2^(-lg2(q)/3) on the SFU.  The float result of MUFU.LG2 is rounded at |lg2 q| <= 64, so the
+    // seed carries up to ~4e-7 relative error for the closest pairs (1e-7 typical): that is what the
+    // velocity-only kernel uses (random in sign; the sums agree with the reference to ~1e-7).  The
+    // gradient-type results also feed K into B, so they take one Newton step  k <- k + k (1 - q k^3)/3
+    // on the FMA pipe.
     const float2 k = make_float2(mufu_ex2(-0.33333334f * mufu_lg2(q.x)), mufu_ex2(-0.33333334f * mufu_lg2(q.y)));
-    const float2 k3 = mul2(mul2(k, k), k);
-    const float2 e = fma2(mul2(f2(-1.0f), q), k3, f2(1.0f));
-    K = fma2(mul2(k, f2(0.33333334f)), e, k);
+    if (GRAD) {
+      const float2 k3 = mul2(mul2(k, k), k);
+      const float2 e = fma2(neg2(q), k3, f2(1.0f));
+      K = fma2(mul2(k, f2(0.33333334f)), e, k);
+    } else {
+      K = k;
+    }
     // q == 0 (coincident zero-radius pair) gives inf*0 above; the reference returns inf there
     if (q.x == 0.0f) K.x = __int_as_float(0x7f800000);
     if (q.y == 0.0f) K.y = __int_as_float(0x7f800000);

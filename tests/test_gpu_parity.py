@@ -405,3 +405,25 @@ def test_points_on_panels_near_far_transition_pointwise(ctx):
     eu, ev = points_on_panels_f64(sx, sy, s, nx, ny, idx, area)
     err = np.hypot(pu - eu, pv - ev) / np.hypot(eu, ev)
     assert err.max() < 3e-6, (err.max(), np.argmax(err))
+
+
+def test_callable_from_a_non_main_thread_with_changing_sizes(ctx, port):
+    """SURVEY 8b 'Threading': the GUI calls the path from a std::async worker, sequentially, with sizes that change
+    between calls (diffusion / merge resize the collections)."""
+    import threading
+    results = {}
+
+    def worker():
+        try:
+            for n in (700, 33, 2500, 1, 1024):
+                sx, sy, ss, sr = W.gaussian_blob(n, seed=n)
+                results[n] = (ctx.points_on_points_np("v2", o2d.VELONLY, sx, sy, ss, sr, sx, sy, sr),
+                              port.points_on_points("v2", oracle.VELONLY, sx, sy, ss, sr, sx, sy, sr))
+        except Exception as e:  # pragma: no cover
+            results["error"] = e
+
+    t = threading.Thread(target=worker)
+    t.start(); t.join()
+    assert "error" not in results, results.get("error")
+    for n, (got, want) in results.items():
+        assert W.rel_err(got, want[:2]) < 1e-5, n

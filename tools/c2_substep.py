@@ -59,8 +59,8 @@ for n in [int(s) for s in args.sizes.split(",")]:
     rows.append((n, "points_affect_panels (BEM right-hand side)", float(n) * NP, gms, cms, W.rel_err(g, c[:2])))
     # clear_inner_layer after a move: pull a tenth of the particles into the layer first
     qx, qy = x.copy(), y.copy()
-    qx[::10] *= 0.5 / np.hypot(x[::10], y[::10]) * 1.01
-    qy[::10] *= 0.5 / np.hypot(x[::10], y[::10]) * 1.01
+    qx[::10] *= 0.5 / np.hypot(x[::10], y[::10]) * 1.004
+    qy[::10] *= 0.5 / np.hypot(x[::10], y[::10]) * 1.004
     gms, g = best(lambda: ctx.clear_inner_layer_np(nx, ny, idx, snx, sny, qx, qy, CF, IPS))
     cms, c = best(lambda: R.clear_inner_layer(nx, ny, idx, qx, qy, CF, IPS), reps=2)
     rows.append((n, f"clear_inner_layer (push; {g[2]} pushes)", float(n) * NP, gms, cms,
