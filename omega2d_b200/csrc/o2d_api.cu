@@ -56,6 +56,9 @@ constexpr int kNcclChar = 0;     // ncclInt8 / ncclChar
 constexpr int kNcclDouble = 8;   // ncclFloat64
 constexpr int kNcclSum = 0;      // ncclSum
 
+constexpr size_t kSmallCopy = 256 * 1024;        // arrays up to this size travel through the pinned buffer
+constexpr size_t kPinBytes = 8 * 1024 * 1024;
+
 #define bind_device o2d_bind_device
 #define drain_timing o2d_drain_timing
 int o2d_bind_device(o2d_context* c) {
@@ -119,6 +122,14 @@ extern "C" int o2d_create(o2d_context** out, int device) {
   CU(cudaEventCreateWithFlags(&c->ev_gather, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming));
   c->stream = c->own_stream;
+  // pinned staging for small host arrays (see o2d_h2d_bytes); without it every copy takes the pageable path
+  void* pin = nullptr;
+  if (cudaHostAlloc(&pin, kPinBytes, cudaHostAllocDefault) == cudaSuccess) {
+    c->pin = static_cast<char*>(pin);
+    c->pin_cap = kPinBytes;
+  } else {
+    (void)cudaGetLastError();
+  }
   *out = c;
   return O2D_OK;
 }
@@ -133,6 +144,7 @@ extern "C" int o2d_destroy(o2d_context* c) {
   for (DevBuf* b : {&c->packed, &c->packed_all, &c->partial, &c->panel_packed, &c->hsrc, &c->htgt, &c->hout, &c->hidx, &c->hpan, &c->adv, &c->coef, &c->counter, &c->vtu})
     b->release();
   if (c->vtu_host) cudaFreeHost(c->vtu_host);
+  if (c->pin) cudaFreeHost(c->pin);
   for (auto& pr : c->ev_pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (auto& pr : c->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   cudaEventDestroy(c->ev_gather);
@@ -152,7 +164,7 @@ extern "C" int o2d_set_stream(o2d_context* c, void* s) {
 extern "C" int o2d_synchronize(o2d_context* c) {
   if (!c) return fail(O2D_ERR_INVALID, "ctx is NULL");
   if (int rc = bind_device(c)) return rc;
-  CU(cudaStreamSynchronize(c->stream));
+  if (int rc_ = o2d_finish_host(c)) return rc_;
   return O2D_OK;
 }
 
@@ -260,14 +272,54 @@ int o2d_pp_device(o2d_context* c, int core, int res,
 }
 
 // ---- host staging helpers ----------------------------------------------------------------------------------
-int o2d_h2d(o2d_context* c, float* dst, const float* src, size_t n) {
-  if (n == 0) return O2D_OK;
-  CU(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+// Host arrays are the caller's pageable std::vector storage.  A pageable cudaMemcpy is staged by the driver and
+// costs ~10 us per call however small; an evaluation moves 10-15 arrays, which is most of the wall time of a
+// 10k-particle call (C1/C2 sizes).  Arrays up to kSmallCopy bytes therefore go through the context's pinned
+// buffer: memcpy + truly asynchronous DMA on the way in; DMA + memcpy after the final synchronise on the way out.
+static char* pin_take(o2d_context* c, size_t bytes) {
+  if (!c->pin || bytes > kSmallCopy) return nullptr;
+  const size_t need = (bytes + 63) / 64 * 64;
+  if (c->pin_off + need > c->pin_cap) return nullptr;
+  char* p = c->pin + c->pin_off;
+  c->pin_off += need;
+  return p;
+}
+// caller memory that is already page-locked (cudaHostAlloc / cudaHostRegister) needs no staging
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+int o2d_h2d_bytes(o2d_context* c, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return O2D_OK;
+  if (bytes <= kSmallCopy && is_pinned(src)) {
+    // fall through to the direct asynchronous copy
+  } else if (char* p = pin_take(c, bytes)) {
+    memcpy(p, src, bytes);
+    src = p;
+  }
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
   return O2D_OK;
 }
-int o2d_d2h(o2d_context* c, float* dst, const float* src, size_t n) {
-  if (n == 0) return O2D_OK;
-  CU(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+int o2d_d2h_bytes(o2d_context* c, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return O2D_OK;
+  if (bytes <= kSmallCopy && is_pinned(dst)) {
+    // direct
+  } else if (char* p = pin_take(c, bytes)) {
+    CU(cudaMemcpyAsync(p, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    c->pending_out.push_back({dst, p, bytes});
+    return O2D_OK;
+  }
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  return O2D_OK;
+}
+int o2d_h2d(o2d_context* c, float* dst, const float* src, size_t n) { return o2d_h2d_bytes(c, dst, src, n * sizeof(float)); }
+int o2d_d2h(o2d_context* c, float* dst, const float* src, size_t n) { return o2d_d2h_bytes(c, dst, src, n * sizeof(float)); }
+int o2d_finish_host(o2d_context* c) {
+  CU(cudaStreamSynchronize(c->stream));
+  for (const auto& po : c->pending_out) memcpy(po.dst, po.src, po.bytes);
+  c->pending_out.clear();
+  c->pin_off = 0;
   return O2D_OK;
 }
 #define h2d o2d_h2d
@@ -276,6 +328,10 @@ int o2d_d2h(o2d_context* c, float* dst, const float* src, size_t n) {
 int o2d_check_common(o2d_context* c, int mem) {
   if (!c) return fail(O2D_ERR_INVALID, "ctx is NULL");
   if (mem != O2D_MEM_HOST && mem != O2D_MEM_DEVICE) return fail(O2D_ERR_INVALID, "unknown mem space %d", mem);
+  if (mem == O2D_MEM_HOST) {       // a host-array call starts with an empty pinned buffer (an earlier call may have failed half way)
+    if (!c->pending_out.empty()) { cudaStreamSynchronize(c->stream); c->pending_out.clear(); }
+    c->pin_off = 0;
+  }
   return bind_device(c);
 }
 #define check_common o2d_check_common
@@ -337,7 +393,7 @@ extern "C" int o2d_points_on_points(o2d_context* c, int core, int results, int m
   if ((rc = o2d_pp_device(c, core, res, ns, dsx, dsy, dss, dsr, nt, dtx, dty, dtr, o))) return rc;
   for (int k = 0; k < nout; ++k)
     if ((rc = d2h(c, outs[k], o.p[k], nt))) return rc;
-  CU(cudaStreamSynchronize(c->stream));
+  if (int rc_ = o2d_finish_host(c)) return rc_;
   return O2D_OK;
 }
 
@@ -367,7 +423,7 @@ extern "C" int o2d_points_vorticity(o2d_context* c, int mem,
     return rc;
   if ((rc = o2d_pp_device(c, CORE_RM, RES_VORT, ns, dsx, dsy, dss, dsr, nt, dtx, dty, nullptr, o))) return rc;
   if ((rc = d2h(c, tw, o.p[0], nt))) return rc;
-  CU(cudaStreamSynchronize(c->stream));
+  if (int rc_ = o2d_finish_host(c)) return rc_;
   return O2D_OK;
 }
 
@@ -436,11 +492,11 @@ extern "C" int o2d_panels_on_points(o2d_context* c, int mem,
       (rc = h2d(c, dtv, tv, nt)))
     return rc;
   if (ss && (rc = h2d(c, dss, ss, np))) return rc;
-  CU(cudaMemcpyAsync(c->hidx.p, idx, (size_t)2 * np * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  if (int rc_ = o2d_h2d_bytes(c, c->hidx.p, idx, (size_t)2 * np * sizeof(uint32_t))) return rc_;
   if ((rc = o2d_panels_on_points_device(c, np, dnx, dny, c->hidx.as<uint32_t>(), dvs, dss, nt, dtx, dty, dtu, dtv)))
     return rc;
   if ((rc = d2h(c, tu, dtu, nt)) || (rc = d2h(c, tv, dtv, nt))) return rc;
-  CU(cudaStreamSynchronize(c->stream));
+  if (int rc_ = o2d_finish_host(c)) return rc_;
   return O2D_OK;
 }
 
@@ -529,11 +585,11 @@ extern "C" int o2d_points_on_panels_sharded(o2d_context* c, int mem,
       (rc = h2d(c, dnx, nx, nnodes)) || (rc = h2d(c, dny, ny, nnodes)) || (rc = h2d(c, darea, area, np)) ||
       (rc = h2d(c, dpu, pu, np)) || (rc = h2d(c, dpv, pv, np)))
     return rc;
-  CU(cudaMemcpyAsync(c->hidx.p, idx, (size_t)2 * np * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  if (int rc_ = o2d_h2d_bytes(c, c->hidx.p, idx, (size_t)2 * np * sizeof(uint32_t))) return rc_;
   if ((rc = points_on_panels_impl(c, ns_local, dsx, dsy, dss, np, dnx, dny, c->hidx.as<uint32_t>(), darea, dpu, dpv, true)))
     return rc;
   if ((rc = d2h(c, pu, dpu, np)) || (rc = d2h(c, pv, dpv, np))) return rc;
-  CU(cudaStreamSynchronize(c->stream));
+  if (int rc_ = o2d_finish_host(c)) return rc_;
   return O2D_OK;
 }
 
@@ -561,11 +617,11 @@ extern "C" int o2d_points_on_panels(o2d_context* c, int mem,
       (rc = h2d(c, dnx, nx, nnodes)) || (rc = h2d(c, dny, ny, nnodes)) || (rc = h2d(c, darea, area, np)) ||
       (rc = h2d(c, dpu, pu, np)) || (rc = h2d(c, dpv, pv, np)))
     return rc;
-  CU(cudaMemcpyAsync(c->hidx.p, idx, (size_t)2 * np * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  if (int rc_ = o2d_h2d_bytes(c, c->hidx.p, idx, (size_t)2 * np * sizeof(uint32_t))) return rc_;
   if ((rc = o2d_points_on_panels_device(c, ns, dsx, dsy, dss, np, dnx, dny, c->hidx.as<uint32_t>(), darea, dpu, dpv)))
     return rc;
   if ((rc = d2h(c, pu, dpu, np)) || (rc = d2h(c, pv, dpv, np))) return rc;
-  CU(cudaStreamSynchronize(c->stream));
+  if (int rc_ = o2d_finish_host(c)) return rc_;
   return O2D_OK;
 }
 
@@ -610,7 +666,7 @@ extern "C" int o2d_finalize_vels(o2d_context* c, int mem, int n, float* u, float
   if ((rc = d2h(c, u, du, n)) || (rc = d2h(c, v, dv, n))) return rc;
   if (w && (rc = d2h(c, w, dw, n))) return rc;
   if (e && (rc = d2h(c, e, de, n))) return rc;
-  CU(cudaStreamSynchronize(c->stream));
+  if (int rc_ = o2d_finish_host(c)) return rc_;
   return O2D_OK;
 }
 
@@ -906,6 +962,6 @@ extern "C" int o2d_points_on_points_sharded(o2d_context* c, int core, int result
   if ((rc = o2d_pp_sharded_device(c, core, res, ns_local, ns_block, dsx, dsy, dss, dsr, nt, dtx, dty, dtr, o))) return rc;
   for (int k = 0; k < nout; ++k)
     if ((rc = d2h(c, outs[k], o.p[k], nt))) return rc;
-  CU(cudaStreamSynchronize(c->stream));
+  if (int rc_ = o2d_finish_host(c)) return rc_;
   return O2D_OK;
 }

@@ -205,13 +205,13 @@ extern "C" int o2d_panels_on_panels_coeff(o2d_context* c, int mem,
   if (both_strengths && ((rc = o2d_h2d(c, dnnx, tnx, ntarg)) || (rc = o2d_h2d(c, dnny, tny, ntarg)))) return rc;
   uint32_t* dsi = c->hidx.as<uint32_t>();
   uint32_t* dti = dsi + 2 * (size_t)nsrc;
-  CU(cudaMemcpyAsync(dsi, sidx, (size_t)2 * nsrc * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(dti, tidx, (size_t)2 * ntarg * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  if (int rc_ = o2d_h2d_bytes(c, dsi, sidx, (size_t)2 * nsrc * sizeof(uint32_t))) return rc_;
+  if (int rc_ = o2d_h2d_bytes(c, dti, tidx, (size_t)2 * ntarg * sizeof(uint32_t))) return rc_;
   if ((rc = coeff_device(c, nsrc, dsnx, dsny, dsi, dsa, ntarg, dtnx, dtny, dti, dta, dttx, dtty, dnnx, dnny,
                          both_strengths, same_surface, dld, c->coef.as<float>())))
     return rc;
   CU(cudaMemcpy2DAsync(coeffs, (size_t)ld * sizeof(float), c->coef.p, dld * sizeof(float), rows * sizeof(float), cols,
                        cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  if (int rc_ = o2d_finish_host(c)) return rc_;
   return O2D_OK;
 }

@@ -56,6 +56,12 @@ struct o2d_context {
   DevBuf vtu;                            // o2d_vtu_points: base64 staging
   void* vtu_host = nullptr;              // o2d_write_vtu_points: pinned file image
   size_t vtu_host_cap = 0;
+  // small host arrays travel through this pinned buffer (see o2d_h2d_bytes): a pageable cudaMemcpy costs
+  // ~10 us of driver staging per call whatever its size, which dominates 10k-particle evaluations
+  char* pin = nullptr;
+  size_t pin_cap = 0, pin_off = 0;
+  struct PendingOut { void* dst; const void* src; size_t bytes; };
+  std::vector<PendingOut> pending_out;   // D2H copies parked in `pin`, delivered by o2d_finish_host
   // comm
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;
@@ -89,8 +95,12 @@ struct Stager {   // carve float arrays out of one device buffer
   }
 };
 inline size_t padded_floats(size_t n) { return ((n * sizeof(float) + 255) / 256) * 256; }
+int o2d_h2d_bytes(o2d_context* c, void* dst, const void* src, size_t bytes);
+int o2d_d2h_bytes(o2d_context* c, void* dst, const void* src, size_t bytes);
 int o2d_h2d(o2d_context* c, float* dst, const float* src, size_t n);
 int o2d_d2h(o2d_context* c, float* dst, const float* src, size_t n);
+// end of a host-array call: wait for the stream, then hand over the small results parked in the pinned buffer
+int o2d_finish_host(o2d_context* c);
 int o2d_check_common(o2d_context* c, int mem);
 
 // ---- device-pointer workers (all arrays in device memory, asynchronous on c->stream) --------------------

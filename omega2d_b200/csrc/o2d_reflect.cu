@@ -224,7 +224,7 @@ static int cil_entry(o2d_context* c, int mode, int mem,
     if (num_moved) {   // the count is the only thing that needs the host: synchronous only when asked for
       unsigned long long h = 0;
       CU(cudaMemcpyAsync(&h, d_moved, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-      CU(cudaStreamSynchronize(c->stream));
+      if (int rc_ = o2d_finish_host(c)) return rc_;
       *num_moved = (long long)h;
     }
     return O2D_OK;
@@ -240,13 +240,13 @@ static int cil_entry(o2d_context* c, int mode, int mem,
   if ((rc = o2d_h2d(c, dnx, nx, nnodes)) || (rc = o2d_h2d(c, dny, ny, nnodes)) || (rc = o2d_h2d(c, dsnx, snx, np)) ||
       (rc = o2d_h2d(c, dsny, sny, np)) || (rc = o2d_h2d(c, dtx, tx, n)) || (rc = o2d_h2d(c, dty, ty, n)))
     return rc;
-  CU(cudaMemcpyAsync(c->hidx.p, idx, (size_t)2 * np * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  if (int rc_ = o2d_h2d_bytes(c, c->hidx.p, idx, (size_t)2 * np * sizeof(uint32_t))) return rc_;
   if ((rc = cil_device(c, mode, np, nnodes, dnx, dny, c->hidx.as<uint32_t>(), dsnx, dsny, n, dtx, dty, cutoff_mult, ips, d_moved)))
     return rc;
   unsigned long long h = 0;
   if ((rc = o2d_d2h(c, tx, dtx, n)) || (rc = o2d_d2h(c, ty, dty, n))) return rc;
   CU(cudaMemcpyAsync(&h, d_moved, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  if (int rc_ = o2d_finish_host(c)) return rc_;
   if (num_moved) *num_moved = (long long)h;
   return O2D_OK;
 }

@@ -110,7 +110,7 @@ extern "C" int o2d_points_status(o2d_context* c, int mem, int n, const float* x,
     CU(cudaGetLastError());
     c->launches += 2;
     CU(cudaMemcpyAsync(h, out, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    if (int rc_ = o2d_finish_host(c)) return rc_;
   }
   if (total_circ) *total_circ = (float)h[0];
   if (impulse_x) *impulse_x = (float)h[1];

@@ -131,7 +131,7 @@ int stage_panels(o2d_context* c, int np, int nnodes, const float* nx, const floa
   int rc;
   if ((rc = o2d_h2d(c, dnx, nx, nnodes)) || (rc = o2d_h2d(c, dny, ny, nnodes)) || (rc = o2d_h2d(c, dvs, vs, np))) return rc;
   if (ss && (rc = o2d_h2d(c, dss, ss, np))) return rc;
-  CU(cudaMemcpyAsync(c->hidx.p, idx, (size_t)2 * np * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  if (int rc_ = o2d_h2d_bytes(c, c->hidx.p, idx, (size_t)2 * np * sizeof(uint32_t))) return rc_;
   d->nx = dnx; d->ny = dny; d->idx = c->hidx.as<uint32_t>(); d->vs = dvs; d->ss = dss;
   return O2D_OK;
 }
@@ -207,7 +207,7 @@ extern "C" int o2d_find_vels(o2d_context* c, int core, int results, int mem,
     return rc;
   if ((rc = o2d_d2h(c, tu, dtu, nt)) || (rc = o2d_d2h(c, tv, dtv, nt))) return rc;
   if (res != RES_U && (rc = o2d_d2h(c, tq, dtq, nt))) return rc;
-  CU(cudaStreamSynchronize(c->stream));
+  if (int rc_ = o2d_finish_host(c)) return rc_;
   return O2D_OK;
 }
 
@@ -254,7 +254,7 @@ extern "C" int o2d_find_vels_sharded(o2d_context* c, int core, int results, int 
     return rc;
   if ((rc = o2d_d2h(c, tu, dtu, nt)) || (rc = o2d_d2h(c, tv, dtv, nt))) return rc;
   if (res != RES_U && (rc = o2d_d2h(c, tq, dtq, nt))) return rc;
-  CU(cudaStreamSynchronize(c->stream));
+  if (int rc_ = o2d_finish_host(c)) return rc_;
   return O2D_OK;
 }
 
@@ -336,6 +336,6 @@ extern "C" int o2d_advect(o2d_context* c, int core, int order, int mem,
   if ((rc = o2d_d2h(c, x, dx, n)) || (rc = o2d_d2h(c, y, dy, n)) || (rc = o2d_d2h(c, u, du, n)) ||
       (rc = o2d_d2h(c, v, dv, n)))
     return rc;
-  CU(cudaStreamSynchronize(c->stream));
+  if (int rc_ = o2d_finish_host(c)) return rc_;
   return O2D_OK;
 }
