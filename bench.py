@@ -460,33 +460,45 @@ def run_ours(args, wl, n1):
     c1 = None
     if world == 1 and not args.no_variants and args.workload == "c3":
         cx, cy, cs, cr = W.c1_speedtest(20000)
-        hx = [torch.from_numpy(a.copy()).pin_memory() for a in (cx, cy, cs, cr)]
-        hu = [torch.zeros(20000).pin_memory() for _ in range(2)]
-        def c1_step():
-            hx[0].copy_(torch.from_numpy(cx)); hx[1].copy_(torch.from_numpy(cy))
-            ctx.advect("v2", 2, o2d.MEM_HOST, 20000, hx[0], hx[1], hx[2], hx[3], hu[0], hu[1], dt=0.005)
+        # pageable host arrays, like the reference's std::vector storage
+        hx = [a.copy() for a in (cx, cy, cs, cr)]
+        hu = [np.zeros(20000, np.float32) for _ in range(2)]
+
+        def c1_run(nsteps):
+            hx[0][:] = cx; hx[1][:] = cy
+            ctx.advect("v2", 2, o2d.MEM_HOST, 20000, hx[0], hx[1], hx[2], hx[3], hu[0], hu[1], dt=0.005, nsteps=nsteps)
         for _ in range(3):
-            c1_step()
+            c1_run(1)
         t0 = time.perf_counter()
         for _ in range(10):
-            c1_step()
+            c1_run(1)
         gpu_ms = (time.perf_counter() - t0) / 10 * 1e3
-        c1 = {"what": "C1 speedtest20kx10 restated: one RK2 (Ralston) convection step of 20k blobs, V2 core, "
-                      "o2d_advect with host arrays (one upload, both stages on the device, one download)",
-              "gpu_ms_per_step": gpu_ms, "pairs_per_step": 2 * 20000.0 ** 2,
-              "gpu_value": 2 * 20000.0 ** 2 / (gpu_ms * 1e-3), "unit": UNIT}
+        c1_run(10)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            c1_run(10)
+        run_ms = (time.perf_counter() - t0) / 3 * 1e3
+        c1 = {"what": "C1 speedtest20kx10 restated (20k blobs, V2 core, inviscid, Ralston RK2, dt 0.005; 2 evaluations of 4e8 pairs "
+                      "per step), pageable host arrays in and out: gpu_ms_per_step = one o2d_advect call per step (upload, both "
+                      "stages on the device, download); gpu_ms_10_steps = the whole 10-step run as ONE o2d_advect_steps call "
+                      "(particles resident on the GPU between steps)",
+              "gpu_ms_per_step": gpu_ms, "gpu_ms_10_steps": run_ms, "pairs_per_step": 2 * 20000.0 ** 2,
+              "gpu_value": 2 * 20000.0 ** 2 / (gpu_ms * 1e-3), "gpu_value_10_steps": 20 * 20000.0 ** 2 / (run_ms * 1e-3), "unit": UNIT}
         if not args.no_cpu_baseline:
             import oracle
             oracle.set_threads()
-            adv = (lambda: oracle.ref("v2").advect(2, cx, cy, cs, cr, 0.005)) if oracle.have_ref() else \
-                  (lambda: oracle.port().advect("v2", 2, cx, cy, cs, cr, 0.005))
-            want = adv()
+            step = (lambda x, y: oracle.ref("v2").advect(2, x, y, cs, cr, 0.005)) if oracle.have_ref() else \
+                   (lambda x, y: oracle.port().advect("v2", 2, x, y, cs, cr, 0.005))
+            step(cx, cy)
             t0 = time.perf_counter()
-            want = adv()
+            wx, wy = cx, cy
+            for _ in range(10):
+                wx, wy, _, _ = step(wx, wy)
             cpu_ms = (time.perf_counter() - t0) * 1e3
-            derr = float(np.abs(np.stack([hx[0].numpy() - want[0], hx[1].numpy() - want[1]])).max())
-            c1.update(cpu_ms_per_step=cpu_ms, cpu_value=2 * 20000.0 ** 2 / (cpu_ms * 1e-3), cpu_cores=oracle.host_cores(),
-                      cpu_kind="reference" if oracle.have_ref() else "port", max_abs_position_diff=derr)
+            derr = float(np.abs(np.stack([hx[0] - wx, hx[1] - wy])).max())
+            c1.update(cpu_ms_10_steps=cpu_ms, cpu_ms_per_step=cpu_ms / 10, cpu_value=20 * 20000.0 ** 2 / (cpu_ms * 1e-3),
+                      cpu_cores=oracle.host_cores(), cpu_kind="reference" if oracle.have_ref() else "port",
+                      max_abs_position_diff_after_10_steps=derr)
 
     # ---- parity spot check + CPU baseline (oracle used as checker / reported baseline only) -------------------
     cpu = None

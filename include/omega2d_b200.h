@@ -179,6 +179,17 @@ int o2d_advect(o2d_context* ctx, int core, int order, int mem,
                const float* pvs, const float* pss, double fsx, double fsy, double dt);
 
 /*
+ * `nsteps` consecutive o2d_advect steps with the particle state resident on the GPU in between: what
+ * Simulation::step does nsteps times for an inviscid particle-only run (reference src/Simulation.cpp:611-742 with
+ * "viscous": "none", e.g. examples/speedtest20kx10.json = 10 steps of 20 000 particles), with one upload before
+ * the first and one download after the last step.  u,v hold what the last step leaves in them.
+ */
+int o2d_advect_steps(o2d_context* ctx, int core, int order, int mem,
+                     int n, float* x, float* y, const float* s, const float* r, float* u, float* v,
+                     int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                     const float* pvs, const float* pss, double fsx, double fsy, double dt, int nsteps);
+
+/*
  * Surfaces::add_solved_rot_strengths / add_rot_strengths_base (reference src/Surfaces.h:556-620), which
  * find_vels applies with factor +1 before and -1 after the sums (src/Convection.h:186-189,219-222):
  * adds to vs,ss the vortex and source sheet strengths equivalent to the solid-body rotation of the

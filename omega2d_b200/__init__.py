@@ -78,6 +78,7 @@ def load_library() -> C.CDLL:
     lib.o2d_find_vels.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp,
                                   i, vp, vp, vp, vp, vp, vp, d, d]
     lib.o2d_advect.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, d, d, d]
+    lib.o2d_advect_steps.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, d, d, d, i]
     lib.o2d_panels_on_panels_coeff.argtypes = [vp, i, i, i, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp,
                                                i, i, C.c_longlong, vp]
     lib.o2d_clear_inner_layer.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp, i, vp, vp, C.c_float, C.c_float,
@@ -315,8 +316,14 @@ class Context:
             int(nt), _ptr(tx), _ptr(ty), _ptr(tr), _ptr(tu), _ptr(tv), _ptr(tq), float(fs[0]), float(fs[1])))
 
     def advect(self, core, order, mem, n, x, y, s, r, u, v, np_=0, nnodes=0, nx=None, ny=None, idx=None,
-               pvs=None, pss=None, fs=(0.0, 0.0), dt=0.0):
+               pvs=None, pss=None, fs=(0.0, 0.0), dt=0.0, nsteps=None):
         core = CORE_ID[core] if isinstance(core, str) else int(core)
+        if nsteps is not None:
+            self._check(self.lib.o2d_advect_steps(
+                self._h, core, int(order), int(mem), int(n), _ptr(x), _ptr(y), _ptr(s), _ptr(r), _ptr(u), _ptr(v),
+                int(np_), int(nnodes), _ptr(nx), _ptr(ny), _ptr(idx), _ptr(pvs), _ptr(pss),
+                float(fs[0]), float(fs[1]), float(dt), int(nsteps)))
+            return
         self._check(self.lib.o2d_advect(
             self._h, core, int(order), int(mem), int(n), _ptr(x), _ptr(y), _ptr(s), _ptr(r), _ptr(u), _ptr(v),
             int(np_), int(nnodes), _ptr(nx), _ptr(ny), _ptr(idx), _ptr(pvs), _ptr(pss),

@@ -305,37 +305,48 @@ static int advect_device(o2d_context* c, int core, int order, int n, float* x, f
   return O2D_OK;
 }
 
-extern "C" int o2d_advect(o2d_context* c, int core, int order, int mem,
-                          int n, float* x, float* y, const float* s, const float* r, float* u, float* v,
-                          int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
-                          const float* pvs, const float* pss, double fsx, double fsy, double dt) {
+extern "C" int o2d_advect_steps(o2d_context* c, int core, int order, int mem,
+                                int n, float* x, float* y, const float* s, const float* r, float* u, float* v,
+                                int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                                const float* pvs, const float* pss, double fsx, double fsy, double dt, int nsteps) {
   if (int rc = o2d_check_common(c, mem)) return rc;
   if (core < 0 || core > 4) return fail(O2D_ERR_INVALID, "unknown core %d", core);
   if (order < 1 || order > 3)
     return fail(O2D_ERR_INVALID, "Convection integrator orders over 3 unsupported (reference src/Convection.h:259)");
-  if (n < 0) return fail(O2D_ERR_INVALID, "negative count");
+  if (n < 0 || nsteps < 0) return fail(O2D_ERR_INVALID, "negative count");
   if (int rc = check_panels(np, nnodes, nx, ny, idx, pvs)) return rc;
-  if (n == 0) return O2D_OK;
+  if (n == 0 || nsteps == 0) return O2D_OK;
   if (!x || !y || !s || !r || !u || !v) return fail(O2D_ERR_INVALID, "NULL particle array");
   Panels pan;
+  int rc;
   if (mem == O2D_MEM_DEVICE) {
     pan.np = np; pan.nx = nx; pan.ny = ny; pan.idx = idx; pan.vs = pvs; pan.ss = pss;
-    return advect_device(c, core, order, n, x, y, s, r, u, v, pan, fsx, fsy, dt);
+    for (int k = 0; k < nsteps; ++k)
+      if ((rc = advect_device(c, core, order, n, x, y, s, r, u, v, pan, fsx, fsy, dt))) return rc;
+    return O2D_OK;
   }
   CU(c->hsrc.reserve(4 * padded_floats(n) + 256));
   CU(c->hout.reserve(kMaxOut * padded_floats(n)));
   Stager S(c, &c->hsrc), O(c, &c->hout);
   float *dx = S.take(n), *dy = S.take(n), *ds = S.take(n), *dr = S.take(n);
   float *du = O.take(n), *dv = O.take(n);
-  int rc;
   if ((rc = o2d_h2d(c, dx, x, n)) || (rc = o2d_h2d(c, dy, y, n)) || (rc = o2d_h2d(c, ds, s, n)) ||
       (rc = o2d_h2d(c, dr, r, n)))
     return rc;
   if ((rc = stage_panels(c, np, nnodes, nx, ny, idx, pvs, pss, &pan))) return rc;
-  if ((rc = advect_device(c, core, order, n, dx, dy, ds, dr, du, dv, pan, fsx, fsy, dt))) return rc;
+  // the particle state stays on the device between the steps: one upload, one download for the whole run
+  for (int k = 0; k < nsteps; ++k)
+    if ((rc = advect_device(c, core, order, n, dx, dy, ds, dr, du, dv, pan, fsx, fsy, dt))) return rc;
   if ((rc = o2d_d2h(c, x, dx, n)) || (rc = o2d_d2h(c, y, dy, n)) || (rc = o2d_d2h(c, u, du, n)) ||
       (rc = o2d_d2h(c, v, dv, n)))
     return rc;
   if (int rc_ = o2d_finish_host(c)) return rc_;
   return O2D_OK;
+}
+
+extern "C" int o2d_advect(o2d_context* c, int core, int order, int mem,
+                          int n, float* x, float* y, const float* s, const float* r, float* u, float* v,
+                          int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                          const float* pvs, const float* pss, double fsx, double fsy, double dt) {
+  return o2d_advect_steps(c, core, order, mem, n, x, y, s, r, u, v, np, nnodes, nx, ny, idx, pvs, pss, fsx, fsy, dt, 1);
 }

@@ -72,13 +72,16 @@ void find_vels(const std::array<double,Dimensions>& _fs,
 // clear_inner_layer are no-ops).  Positions move in place; the velocity arrays end up holding what
 // the reference leaves there (the weighted stage velocities).
 template <class S>
-void advect_particles(const int _order, const double _dt, const std::array<double,Dimensions>& _fs, Points<S>& _pts) {
+void advect_particles(const int _order, const double _dt, const std::array<double,Dimensions>& _fs, Points<S>& _pts,
+                      const int _nsteps = 1) {
+  // _nsteps > 1: that many steps with the particles resident on the GPU in between (an inviscid particle-only run,
+  // e.g. the 10 steps of examples/speedtest20kx10.json, is nothing else): one upload, one download
   auto& x = _pts.get_pos();
   auto& u = _pts.get_vel();
-  o2d_host::check(o2d_advect(o2d_host::device(), o2d_host::selected_core(), _order, O2D_MEM_HOST, (int)_pts.get_n(),
-                             x[0].data(), x[1].data(), _pts.get_str().data(), _pts.get_rad().data(),
-                             u[0].data(), u[1].data(), 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
-                             _fs[0], _fs[1], _dt),
+  o2d_host::check(o2d_advect_steps(o2d_host::device(), o2d_host::selected_core(), _order, O2D_MEM_HOST, (int)_pts.get_n(),
+                                   x[0].data(), x[1].data(), _pts.get_str().data(), _pts.get_rad().data(),
+                                   u[0].data(), u[1].data(), 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                   _fs[0], _fs[1], _dt, _nsteps),
                   "advect_particles");
 }
 

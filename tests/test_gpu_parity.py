@@ -291,6 +291,25 @@ def test_advect_c1_speedtest_vs_oracle(ctx, port):
     check_step(got, want, x, y, TOL)
 
 
+def test_advect_steps_equals_repeated_steps_and_tracks_the_oracle(ctx, port):
+    """o2d_advect_steps keeps the particles on the device between steps: same bits as step-by-step calls; ten RK2 steps
+    of the C1 speedtest (what examples/speedtest20kx10.json runs) stay within tolerance of the CPU restatement."""
+    x, y, s, r = W.c1_speedtest(20000)
+    gx, gy = x.copy(), y.copy()
+    u, v = np.zeros_like(x), np.zeros_like(x)
+    ctx.advect("v2", 2, o2d.MEM_HOST, x.size, gx, gy, s, r, u, v, dt=0.005, nsteps=10)
+    sx_, sy_ = x.copy(), y.copy()
+    su, sv = np.zeros_like(x), np.zeros_like(x)
+    wx, wy = x, y
+    for _ in range(10):
+        ctx.advect("v2", 2, o2d.MEM_HOST, x.size, sx_, sy_, s, r, su, sv, dt=0.005)
+        wx, wy, wu, wv = port.advect("v2", 2, wx, wy, s, r, 0.005)
+    assert np.array_equal(gx, sx_) and np.array_equal(gy, sy_) and np.array_equal(u, su) and np.array_equal(v, sv)
+    assert np.hypot(gx - wx, gy - wy).max() < TOL * 4.0          # domain is [-2,2]^2
+    assert W.rel_err((u, v), (wu, wv)) < 10 * TOL                 # ten steps of accumulated position differences
+    assert np.hypot(gx - x, gy - y).max() > 1e-3                  # and the particles did move
+
+
 def test_advect_device_memory_equals_host_path(ctx):
     import torch
     x, y, s, r = W.c1_speedtest(5000, seed=3)
