@@ -12,6 +12,18 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run by the driver with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """A fresh checkout has no built artefacts (they are git-ignored): compile the product library and the C
+    restatement once, exactly as __graft_entry__.build() does.  This is harness convenience only -- the product
+    itself never builds or falls back at run time (omega2d_b200.load_library raises when the .so is missing)."""
+    import shutil
+    import omega2d_b200 as o2d
+    if not os.path.exists(o2d.LIB_PATH) and shutil.which("nvcc"):
+        o2d.build()
+    import oracle
+    oracle.build_port()
+
+
 @pytest.fixture(scope="session")
 def golden():
     import numpy as np
