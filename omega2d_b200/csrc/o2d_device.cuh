@@ -221,6 +221,30 @@ __device__ __forceinline__ void exp_core_lane(float d2, float sig2, float& K, fl
   }
 }
 
+// The same function for the velocity-only kernels, both lanes at once and without branches: when one pair of a
+// warp's 64 is close enough to need the exponential, all of them run this, so its cost -- not its frequency
+// (3.6 % of the warp steps of a 1M-particle blob) -- is what the kernel pays for.  6 MUFU + 14 packed FP32 ops.
+__device__ __forceinline__ float2 exp_core_pair(float2 d2, float2 sig2) {
+  const float2 ood2 = rcp2(d2);
+  const float2 corefac = rcp2(sig2);
+  const float2 x = mul2(d2, corefac);
+  const float2 t = mul2(f2(-1.4426950408889634f), x);
+  const float2 e = make_float2(mufu_ex2(t.x), mufu_ex2(t.y));
+  float2 p = fma2(f2(-1.0f / 40320.0f), x, f2(1.0f / 5040.0f));     // 1-exp(-x) = x P(x), x < 0.5 (as exp_core_lane)
+  p = fma2(p, x, f2(-1.0f / 720.0f));
+  p = fma2(p, x, f2(1.0f / 120.0f));
+  p = fma2(p, x, f2(-1.0f / 24.0f));
+  p = fma2(p, x, f2(1.0f / 6.0f));
+  p = fma2(p, x, f2(-0.5f));
+  p = fma2(p, x, f2(1.0f));
+  const float2 ser = mul2(x, p);
+  const float2 dir = add2(f2(1.0f), neg2(e));
+  const float2 em1 = make_float2(x.x < 0.5f ? ser.x : dir.x, x.y < 0.5f ? ser.y : dir.y);
+  const float2 mid = mul2(ood2, em1);
+  return make_float2(x.x > 16.0f ? ood2.x : (x.x < 0.001f ? corefac.x : mid.x),
+                     x.y > 16.0f ? ood2.y : (x.y < 0.001f ? corefac.y : mid.y));
+}
+
 // ---- core functions on packed lanes ----------------------------------------------------------
 // Inputs per lane: dx,dy = target - source, rho = source radius term, tau = target radius term.
 // Outputs: K (the reference's core_func return / *r2), d2 = dx^2+dy^2 (only valid when GRAD or
@@ -232,7 +256,7 @@ __device__ __forceinline__ void exp_core_lane(float d2, float sig2, float& K, fl
 // lane-ops, moving the kernel off the FMA pipe and onto the 16/clk/SM MUFU bound alone).
 template <int CORE, bool GRAD, bool UNI>
 __device__ __forceinline__ void core_eval(float2 dx, float2 dy, float2 rho, float2 tau,
-                                          float2& K, float2& B, float2& d2) {
+                                          float2& K, float2& B, float2& d2, float lim = 0.0f) {
   if (CORE == CORE_RM) {
     // src/CoreFunc.h:54-58,74-80: K = 1/(d2 + sr^2 + tr^2), bbb = -2 K^2
     float2 q;
@@ -284,18 +308,22 @@ __device__ __forceinline__ void core_eval(float2 dx, float2 dy, float2 rho, floa
     if (GRAD) B = mul2(fma2(mul2(f2(-4.0f), K), D, f2(2.0f)), mul2(r, r));
   } else {  // CORE_EXP
     d2 = fma2(dy, dy, mul2(dx, dx));
-    const float2 sig2 = UNI ? rho : add2(rho, tau);
     // The reference's first branch (src/CoreFunc.h:118-130: d2/sig2 > 16 -> K = 1/d2) is what almost every
     // pair of a large particle set takes, and it needs one MUFU instead of three.  Taken warp-wide (the
-    // callers are convergent: every thread of the CTA walks the same source pairs).  The gradient factor keeps
-    // a corefac*exp(-x) term in that branch (x exp(-x) = 1.8e-6 at x = 16): it is dropped only beyond x = 24,
+    // callers are convergent: every thread of the CTA walks the same source pairs) on a test that costs no
+    // arithmetic: `lim` = 16 x (largest source radius term of the staged tile + this target's), so d2 > lim
+    // implies d2/sig2 > 16 for the pair; pairs between their own limit and the tile's take the general path,
+    // which evaluates the reference's branches per lane.  The gradient factor keeps a corefac*exp(-x) term in
+    // the far branch (x exp(-x) = 1.8e-6 at x = 16): it is dropped only beyond x = 24 (lim is 24 x ... there),
     // where it is below half an ulp of the 1/d2 term.
-    const float2 lim = mul2(f2(GRAD ? 24.0f : 16.0f), sig2);
-    const bool far = (d2.x > lim.x) && (d2.y > lim.y);
+    const bool far = (d2.x > lim) && (d2.y > lim);
     if (__all_sync(0xffffffffu, far)) {
       K = rcp2(d2);
       if (GRAD) B = mul2(mul2(f2(-2.0f), K), K);
+    } else if (!GRAD) {
+      K = exp_core_pair(d2, UNI ? rho : add2(rho, tau));
     } else {
+      const float2 sig2 = UNI ? rho : add2(rho, tau);
       exp_core_lane<GRAD>(d2.x, sig2.x, K.x, B.x);
       exp_core_lane<GRAD>(d2.y, sig2.y, K.y, B.y);
     }

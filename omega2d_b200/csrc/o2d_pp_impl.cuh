@@ -69,10 +69,16 @@ __device__ __forceinline__ void apply_outputs(const OutPtrs& o, int i, const dou
 
 // Sum one staged tile of TILE sources onto the thread's R targets (float partial sums, two lanes).
 // UNI = all R targets share one radius term (see core_eval): rho+tau is formed once per source pair.
+// rho_max (EXP core only): the largest source radius term of this tile, for the far test of core_eval.
 template <int CORE, int RES, int TILE, int R, int UNROLL, bool UNI>
 __device__ __forceinline__ void tile_sum(const float4* __restrict__ s, const float2 (&tx)[R], const float2 (&ty)[R],
-                                         const float2 (&tau)[R], float2 (&part)[R][ResTraits<RES>::NCOMP]) {
+                                         const float2 (&tau)[R], float2 (&part)[R][ResTraits<RES>::NCOMP],
+                                         const float rho_max) {
   using T = ResTraits<RES>;
+  // EXP: beyond d2 > lim[k] every pair of this tile with target k is in the reference's "d2/sig2 > 16" branch
+  float lim[R];
+#pragma unroll
+  for (int k = 0; k < R; ++k) lim[k] = (T::GRAD ? 24.0f : 16.0f) * (rho_max + tau[k].x);
 #pragma unroll UNROLL
   for (int p = 0; p < TILE / 2; ++p) {
     const float4 A = s[2 * p];      // x0 x1 y0 y1   (stored NEGATED: dx = tx + (-sx))
@@ -92,7 +98,7 @@ __device__ __forceinline__ void tile_sum(const float4* __restrict__ s, const flo
         part[k][0] = fma2(str, e, part[k][0]);
       } else {
         float2 K, Bb, d2;
-        core_eval<CORE, T::GRAD, UNI>(dx, dy, rho, tau[k], K, Bb, d2);
+        core_eval<CORE, T::GRAD, UNI>(dx, dy, rho, tau[k], K, Bb, d2, lim[k]);
         const float2 r2 = mul2(str, K);
         part[k][0] = fma2(r2, dy, part[k][0]);
         part[k][1] = fma2(r2, dx, part[k][1]);
@@ -129,6 +135,7 @@ pp_kernel(const PPArgs a) {
   float4* stage0 = reinterpret_cast<float4*>(smem_raw);
   float4* stage1 = reinterpret_cast<float4*>(smem_raw + TILE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * TILE_BYTES);
+  __shared__ float wmax[2 * (THREADS / 32)];   // EXP core: per-warp maxima of the tile's radius terms, double buffered
 
   const int tid = threadIdx.x;
   const int tile_begin = a.tile_begin + blockIdx.y * a.tiles_per_chunk;
@@ -191,14 +198,27 @@ pp_kernel(const PPArgs a) {
     mbar_wait(&bars[t & 1], (uint32_t)((t >> 1) & 1));
     const float4* s = (t & 1) ? stage1 : stage0;
 
+    // EXP core: largest source radius term of the tile (CTA-wide max of the rho lanes; radius terms are >= 0)
+    float rho_max = 0.0f;
+    if (CORE == CORE_EXP && RES != RES_VORT) {
+      float m = 0.0f;
+      for (int p = tid; p < TILE / 2; p += THREADS) { const float4 B = s[2 * p + 1]; m = fmaxf(m, fmaxf(B.z, B.w)); }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+      if ((tid & 31) == 0) wmax[(t & 1) * (THREADS / 32) + (tid >> 5)] = m;
+      __syncthreads();
+#pragma unroll
+      for (int w = 0; w < THREADS / 32; ++w) rho_max = fmaxf(rho_max, wmax[(t & 1) * (THREADS / 32) + w]);
+    }
+
     float2 part[R][NC];
 #pragma unroll
     for (int k = 0; k < R; ++k)
 #pragma unroll
       for (int c = 0; c < NC; ++c) part[k][c] = f2(0.0f);
 
-    if (uni) tile_sum<CORE, RES, TILE, R, UNROLL, true>(s, tx, ty, tau, part);
-    else     tile_sum<CORE, RES, TILE, R, UNROLL, false>(s, tx, ty, tau, part);
+    if (uni) tile_sum<CORE, RES, TILE, R, UNROLL, true>(s, tx, ty, tau, part, rho_max);
+    else     tile_sum<CORE, RES, TILE, R, UNROLL, false>(s, tx, ty, tau, part, rho_max);
     // fold this tile's float partial sums into the float64 accumulators
 #pragma unroll
     for (int k = 0; k < R; ++k)
