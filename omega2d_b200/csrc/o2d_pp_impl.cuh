@@ -67,6 +67,32 @@ __device__ __forceinline__ void apply_outputs(const OutPtrs& o, int i, const dou
   }
 }
 
+// one source pair's terms onto one target's float partial sums (component lists: ResTraits above)
+template <int RES>
+__device__ __forceinline__ void pair_accumulate(float2 (&part)[ResTraits<RES>::NCOMP], float2 str, float2 K, float2 Bb,
+                                                float2 dx, float2 dy, float2 d2) {
+  const float2 r2 = mul2(str, K);
+  part[0] = fma2(r2, dy, part[0]);
+  part[1] = fma2(r2, dx, part[1]);
+  if (RES == RES_UW) {
+    const float2 bb = mul2(str, Bb);
+    part[2] = fma2(bb, d2, part[2]);
+    part[3] = add2(part[3], r2);
+  } else if (RES == RES_UE) {
+    const float2 bb = mul2(str, Bb);
+    const float2 ab = make_float2(fabsf(bb.x), fabsf(bb.y));
+    part[2] = fma2(ab, d2, part[2]);
+  } else if (RES == RES_UG) {
+    const float2 bb = mul2(str, Bb);
+    const float2 bx = mul2(bb, dx);
+    const float2 by = mul2(bb, dy);
+    part[2] = fma2(bx, dy, part[2]);
+    part[3] = fma2(bx, dx, part[3]);
+    part[4] = fma2(by, dy, part[4]);
+    part[5] = add2(part[5], r2);
+  }
+}
+
 // Sum one staged tile of TILE sources onto the thread's R targets (float partial sums, two lanes).
 // UNI = all R targets share one radius term (see core_eval): rho+tau is formed once per source pair.
 // rho_max (EXP core only): the largest source radius term of this tile, for the far test of core_eval.
@@ -86,6 +112,36 @@ __device__ __forceinline__ void tile_sum(const float4* __restrict__ s, const flo
     const float2 nsx = f2(A.x, A.y), nsy = f2(A.z, A.w);
     const float2 str = f2(B.x, B.y);
     const float2 rho = (UNI && RES != RES_VORT) ? add2(f2(B.z, B.w), tau[0]) : f2(B.z, B.w);
+    if (CORE == CORE_EXP && RES != RES_VORT) {
+      // compact-exponential core: ONE warp vote per source pair decides whether all R targets of all lanes are in
+      // the reference's far branch (K = 1/d2); only the few source pairs that have a close target anywhere in the
+      // warp go through core_eval's per-target test and general path
+      float2 dxk[R], dyk[R], d2k[R];
+      bool allfar = true;
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        dxk[k] = add2(tx[k], nsx);
+        dyk[k] = add2(ty[k], nsy);
+        d2k[k] = fma2(dyk[k], dyk[k], mul2(dxk[k], dxk[k]));
+        allfar = allfar && (d2k[k].x > lim[k]) && (d2k[k].y > lim[k]);
+      }
+      if (__all_sync(0xffffffffu, allfar)) {
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          const float2 K = rcp2(d2k[k]);
+          const float2 Bb = T::GRAD ? mul2(mul2(f2(-2.0f), K), K) : f2(0.0f);
+          pair_accumulate<RES>(part[k], str, K, Bb, dxk[k], dyk[k], d2k[k]);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          float2 K, Bb, d2;
+          core_eval<CORE, T::GRAD, UNI>(dxk[k], dyk[k], rho, tau[k], K, Bb, d2, lim[k]);
+          pair_accumulate<RES>(part[k], str, K, Bb, dxk[k], dyk[k], d2);
+        }
+      }
+      continue;
+    }
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       const float2 dx = add2(tx[k], nsx);
@@ -99,26 +155,7 @@ __device__ __forceinline__ void tile_sum(const float4* __restrict__ s, const flo
       } else {
         float2 K, Bb, d2;
         core_eval<CORE, T::GRAD, UNI>(dx, dy, rho, tau[k], K, Bb, d2, lim[k]);
-        const float2 r2 = mul2(str, K);
-        part[k][0] = fma2(r2, dy, part[k][0]);
-        part[k][1] = fma2(r2, dx, part[k][1]);
-        if (RES == RES_UW) {
-          const float2 bb = mul2(str, Bb);
-          part[k][2] = fma2(bb, d2, part[k][2]);
-          part[k][3] = add2(part[k][3], r2);
-        } else if (RES == RES_UE) {
-          const float2 bb = mul2(str, Bb);
-          const float2 ab = make_float2(fabsf(bb.x), fabsf(bb.y));
-          part[k][2] = fma2(ab, d2, part[k][2]);
-        } else if (RES == RES_UG) {
-          const float2 bb = mul2(str, Bb);
-          const float2 bx = mul2(bb, dx);
-          const float2 by = mul2(bb, dy);
-          part[k][2] = fma2(bx, dy, part[k][2]);
-          part[k][3] = fma2(bx, dx, part[k][3]);
-          part[k][4] = fma2(by, dy, part[k][4]);
-          part[k][5] = add2(part[k][5], r2);
-        }
+        pair_accumulate<RES>(part[k], str, K, Bb, dx, dy, d2);
       }
     }
   }
