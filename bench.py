@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- Biot-Savart pair interactions per second on B200 (BASELINE.json's metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c1|c5|c3grad]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c3vel|c1|c4|c5|v2]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one evaluation of the hot path over one synthetic particle set: the
@@ -9,7 +9,9 @@ points-on-points direct sum that Convection::find_vels runs per Runge-Kutta subs
 (reference src/Convection.h:172-223 -> src/Influence.h:347-361).
 
 Default workload (N=1): BASELINE.json configs[2], "C3": 1M-particle Gaussian vortex blob,
-Rosenhead-Moore core, per-particle radii, velocity on blob targets (kernelu_0v_0b): 1e12 pairs/step.
+Rosenhead-Moore core, per-particle radii, velocity + gradient on blob targets (kernelug_0v_0b): 1e12 pairs/step.
+The velocity-only evaluation of the same particles (kernelu_0v_0b, what find_vels runs per substep) is reported
+under `variants` (and is `--workload c3vel`).
 At N>1 GPUs the particle count follows the weak-scaling recipe of SURVEY 8d/C5 (N_P = N_1 sqrt(P),
 constant pairs per GPU); targets are sharded in contiguous blocks and every rank's packed source
 block is all-gathered once per step over NVLink (o2d_points_on_points_sharded).
@@ -44,11 +46,11 @@ UNIT = "interactions/s"
 
 WORKLOADS = {
     # name: (generator, core, results, description)
-    "c3": dict(n=1_000_000, core="rm", results=1, blob=True,
+    "c3": dict(n=1_000_000, core="rm", results=2, blob=True,
                desc="C3: synthetic 1M-particle Gaussian vortex blob, Rosenhead-Moore core, per-particle radii, "
-                    "velocity on blob targets (kernelu_0v_0b)"),
-    "c3grad": dict(n=1_000_000, core="rm", results=2, blob=True,
-                   desc="C3: 1M-particle Gaussian vortex blob, Rosenhead-Moore core, velocity + gradient (kernelug_0v_0b)"),
+                    "velocity + gradient on blob targets (kernelug_0v_0b: u, v and the 2x2 velocity gradient)"),
+    "c3vel": dict(n=1_000_000, core="rm", results=1, blob=True,
+                  desc="C3 particles, velocity only on blob targets (kernelu_0v_0b: what find_vels evaluates every substep)"),
     "c1": dict(n=20_000, core="v2", results=1, blob=True,
                desc="C1: speedtest20kx10 restated, 20k blobs, Vatistas-2 core, velocity"),
     "c4": dict(n=4_194_304, core="rm", results=1, blob=True, panels=(4, 5000), scaling="strong",
@@ -107,11 +109,11 @@ def cpu_checker(core: str, panels=None):
         r = oracle.ref(core)
         if panels is not None:
             return "reference", (lambda res, sx, sy, ss, sr, tx, ty, tr: r.find_vels(res, (sx, sy, ss, sr), panels, tx, ty, tr))
-        return "reference", (lambda res, *a: r.points_on_points(res, *a))
+        return "reference", (lambda res, *a: r.points_on_points_grad(*a) if res == 2 else r.points_on_points(res, *a))
     p = oracle.port()
     if panels is not None:
         return "port", (lambda res, sx, sy, ss, sr, tx, ty, tr: p.find_vels(core, res, (sx, sy, ss, sr), panels, tx, ty, tr))
-    return "port", (lambda res, *a: p.points_on_points(core, res, *a))
+    return "port", (lambda res, *a: p.points_on_points_grad(core, *a) if res == 2 else p.points_on_points(core, res, *a))
 
 
 def cpu_sample(wl, parts, seconds: float):
@@ -123,7 +125,9 @@ def cpu_sample(wl, parts, seconds: float):
     oracle.set_threads()          # torchrun exports OMP_NUM_THREADS=1; use every host core
     sx, sy, ss, sr = parts
     n = sx.size
-    res = 1 if wl["results"] == 2 else wl["results"]   # the reference has no velandgrad loop
+    # velocity + gradient: the reference defines the pair kernel (kernelug_0v_0b) but no loop drives it;
+    # the CPU arm is that kernel inside the reference's own loop shape, OpenMP over targets (oracle/ref_driver.cpp)
+    res = wl["results"]
 
     def run(count):
         sub = W.strided_subset(n, count)
@@ -425,9 +429,9 @@ def run_ours(args, wl, n1):
     variants = None
     if world == 1 and not args.no_variants and args.workload == "c3":
         variants = []
-        for vname, vcore, vres, vary in (("uniform radius 1.5/sqrt(N) (SURVEY 8d C3 as written; the reference's normal case)", "rm", 1, False),
-                                         ("velocity + gradient (kernelug_0v_0b), per-particle radii", "rm", 2, True),
-                                         ("Vatistas-2 core (reference default), uniform radius", "v2", 1, False)):
+        for vname, vcore, vres, vary in (("velocity only (kernelu_0v_0b: what find_vels evaluates every substep), per-particle radii", "rm", 1, True),
+                                         ("velocity only, uniform radius 1.5/sqrt(N) (the reference's normal case)", "rm", 1, False),
+                                         ("velocity only, Vatistas-2 core (reference default), uniform radius", "v2", 1, False)):
             vp = make_particles(args.workload, n, vary_radius=vary)
             vd = [torch.from_numpy(a).to(dev) for a in vp]
             vn = {1: 2, 2: 6}[vres]
@@ -507,9 +511,14 @@ def run_ours(args, wl, n1):
         dt, sub, ref_out = run(count)
         scale = np.sqrt(u.astype(np.float64) ** 2 + v.astype(np.float64) ** 2).max()
         err = np.sqrt((u[sub] - ref_out[0]).astype(np.float64) ** 2 + (v[sub] - ref_out[1]).astype(np.float64) ** 2).max() / scale
+        if results == 2:      # every gradient component, same form of the tolerance
+            for k in range(2, 6):
+                g = outs[k][:nloc].cpu().numpy().astype(np.float64)
+                err = max(err, float(np.abs(g[sub] - ref_out[k]).max() / np.abs(g).max()))
         import oracle
         cpu = {"value": count * sources_per_target(wl, n) / dt, "unit": UNIT, "cores": oracle.host_cores(), "kind": kind,
-               "sample": f"{count} strided targets x all {n} sources, one call, OpenMP on all host cores, USE_VC off",
+               "sample": f"{count} strided targets x all {n} sources, one call, OpenMP on all host cores, USE_VC off"
+                         + ("; the reference's kernelug_0v_0b in its own loop shape (it ships no velandgrad loop)" if results == 2 else ""),
                "seconds": dt, "max_rel_err_gpu_vs_cpu": float(err), "tolerance": 1e-5}
 
     line = {

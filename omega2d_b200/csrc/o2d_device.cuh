@@ -254,13 +254,22 @@ __device__ __forceinline__ float2 exp_core_pair(float2 d2, float2 sig2) {
 // uniform-radius particle set); `rho` then already holds rho + tau, formed once per source pair and
 // shared by the thread's R targets, which removes one FP32 op per pair (RM velocity: 8 -> 7.25
 // lane-ops, moving the kernel off the FMA pipe and onto the 16/clk/SM MUFU bound alone).
-template <int CORE, bool GRAD, bool UNI>
+//
+// Deferred gradient factor (kBbDeferred): for RM and V2 the reference's bbb is -2 K times something cheap
+// (RM: bbb = -2 K K;  V2: bbb = -2 K (K^2 d2)), so those cores return B = bbb / (-2 K) and the caller forms
+// bb = (ss K) B from the r2 = ss K it needs anyway; the factor -2 is applied once per tile when the float partial
+// sums are folded into float64 (pp_kernel).  Saves two FP32 ops per pair on the gradient-type results.
+template <int CORE> struct CoreTraits { static constexpr bool kBbDeferred = (CORE == CORE_RM || CORE == CORE_V2); };
+
+// NEED_D2 = false: the caller does not read d2 (velocity + gradient accumulates bb dx dy, bb dx^2, bb dy^2 only),
+// which lets RM fold the squares straight into q.
+template <int CORE, bool GRAD, bool UNI, bool NEED_D2 = true>
 __device__ __forceinline__ void core_eval(float2 dx, float2 dy, float2 rho, float2 tau,
                                           float2& K, float2& B, float2& d2, float lim = 0.0f) {
   if (CORE == CORE_RM) {
     // src/CoreFunc.h:54-58,74-80: K = 1/(d2 + sr^2 + tr^2), bbb = -2 K^2
     float2 q;
-    if (GRAD) {
+    if (GRAD && NEED_D2) {
       d2 = fma2(dy, dy, mul2(dx, dx));
       q = UNI ? add2(d2, rho) : add2(add2(d2, tau), rho);
     } else if (UNI) {
@@ -269,13 +278,13 @@ __device__ __forceinline__ void core_eval(float2 dx, float2 dy, float2 rho, floa
       q = add2(fma2(dy, dy, fma2(dx, dx, tau)), rho);   // 3 FP32 ops, no separate d2
     }
     K = rcp2(q);
-    if (GRAD) B = mul2(mul2(f2(-2.0f), K), K);
+    if (GRAD) B = K;                                     // deferred: bbb / (-2 K)
   } else if (CORE == CORE_V2) {
     // src/CoreFunc.h:245-250,266-273: K = rsqrt(d2^2 + sr^4 + tr^4), bbb = -2 K^3 d2
     d2 = fma2(dy, dy, mul2(dx, dx));
     const float2 q = UNI ? fma2(d2, d2, rho) : add2(fma2(d2, d2, tau), rho);
     K = rsqrt2(q);
-    if (GRAD) B = mul2(mul2(mul2(f2(-2.0f), K), mul2(K, K)), d2);
+    if (GRAD) B = mul2(mul2(K, K), d2);                  // deferred: bbb / (-2 K)
   } else if (CORE == CORE_V3) {
     // src/CoreFunc.h:290-295,312-320: K = cbrt(d2^3 + sr^6 + tr^6)^-1, bbb = -2 d2^2 K / (d2^3+..)
     d2 = fma2(dy, dy, mul2(dx, dx));

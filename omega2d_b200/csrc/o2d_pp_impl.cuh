@@ -67,23 +67,35 @@ __device__ __forceinline__ void apply_outputs(const OutPtrs& o, int i, const dou
   }
 }
 
+// factor applied to component c when a tile's float partial sums are folded into float64: the deferred -2 of the
+// gradient factor for the components built from bb (|bb| for the shear rate), 1 otherwise
+template <int CORE, int RES>
+__device__ __forceinline__ constexpr double bb_fold_scale(int c) {
+  if (!CoreTraits<CORE>::kBbDeferred) return 1.0;
+  if (RES == RES_UW && c == 2) return -2.0;
+  if (RES == RES_UE && c == 2) return 2.0;
+  if (RES == RES_UG && (c == 2 || c == 3 || c == 4)) return -2.0;
+  return 1.0;
+}
+
 // one source pair's terms onto one target's float partial sums (component lists: ResTraits above)
-template <int RES>
+// DEFER: Bb is the deferred gradient factor of core_eval (bb = r2 * Bb, the -2 applied at the float64 fold)
+template <int RES, bool DEFER>
 __device__ __forceinline__ void pair_accumulate(float2 (&part)[ResTraits<RES>::NCOMP], float2 str, float2 K, float2 Bb,
                                                 float2 dx, float2 dy, float2 d2) {
   const float2 r2 = mul2(str, K);
   part[0] = fma2(r2, dy, part[0]);
   part[1] = fma2(r2, dx, part[1]);
   if (RES == RES_UW) {
-    const float2 bb = mul2(str, Bb);
+    const float2 bb = mul2(DEFER ? r2 : str, Bb);
     part[2] = fma2(bb, d2, part[2]);
     part[3] = add2(part[3], r2);
   } else if (RES == RES_UE) {
-    const float2 bb = mul2(str, Bb);
+    const float2 bb = mul2(DEFER ? r2 : str, Bb);
     const float2 ab = make_float2(fabsf(bb.x), fabsf(bb.y));
     part[2] = fma2(ab, d2, part[2]);
   } else if (RES == RES_UG) {
-    const float2 bb = mul2(str, Bb);
+    const float2 bb = mul2(DEFER ? r2 : str, Bb);
     const float2 bx = mul2(bb, dx);
     const float2 by = mul2(bb, dy);
     part[2] = fma2(bx, dy, part[2]);
@@ -130,14 +142,14 @@ __device__ __forceinline__ void tile_sum(const float4* __restrict__ s, const flo
         for (int k = 0; k < R; ++k) {
           const float2 K = rcp2(d2k[k]);
           const float2 Bb = T::GRAD ? mul2(mul2(f2(-2.0f), K), K) : f2(0.0f);
-          pair_accumulate<RES>(part[k], str, K, Bb, dxk[k], dyk[k], d2k[k]);
+          pair_accumulate<RES, false>(part[k], str, K, Bb, dxk[k], dyk[k], d2k[k]);
         }
       } else {
 #pragma unroll
         for (int k = 0; k < R; ++k) {
           float2 K, Bb, d2;
           core_eval<CORE, T::GRAD, UNI>(dxk[k], dyk[k], rho, tau[k], K, Bb, d2, lim[k]);
-          pair_accumulate<RES>(part[k], str, K, Bb, dxk[k], dyk[k], d2);
+          pair_accumulate<RES, false>(part[k], str, K, Bb, dxk[k], dyk[k], d2);
         }
       }
       continue;
@@ -154,8 +166,8 @@ __device__ __forceinline__ void tile_sum(const float4* __restrict__ s, const flo
         part[k][0] = fma2(str, e, part[k][0]);
       } else {
         float2 K, Bb, d2;
-        core_eval<CORE, T::GRAD, UNI>(dx, dy, rho, tau[k], K, Bb, d2, lim[k]);
-        pair_accumulate<RES>(part[k], str, K, Bb, dx, dy, d2);
+        core_eval<CORE, T::GRAD, UNI, RES != RES_UG>(dx, dy, rho, tau[k], K, Bb, d2, lim[k]);
+        pair_accumulate<RES, CoreTraits<CORE>::kBbDeferred>(part[k], str, K, Bb, dx, dy, d2);
       }
     }
   }
@@ -260,7 +272,10 @@ pp_kernel(const PPArgs a) {
 #pragma unroll
     for (int k = 0; k < R; ++k)
 #pragma unroll
-      for (int c = 0; c < NC; ++c) acc[k][c] += (double)part[k][c].x + (double)part[k][c].y;
+      for (int c = 0; c < NC; ++c) {
+        const double sum = (double)part[k][c].x + (double)part[k][c].y;
+        acc[k][c] += bb_fold_scale<CORE, RES>(c) * sum;
+      }
   }
 
   // ---- epilogue -----------------------------------------------------------------------------------
