@@ -254,6 +254,15 @@ def run_ours(args, wl, n1):
         raise SystemExit("bench.py: no CUDA device; omega2d_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # stdout carries exactly ONE JSON line: whatever libraries print while communicators come up (NCCL's version
+    # banner under NCCL_DEBUG=VERSION, for one) is sent to stderr at the file-descriptor level until the line is due
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def restore_stdout():
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -401,6 +410,7 @@ def run_ours(args, wl, n1):
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
+        restore_stdout()
         return
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------------
@@ -537,10 +547,13 @@ def run_ours(args, wl, n1):
         "frac_fp32_peak_whole_step": (flops_pp * float(n) * float(n) + panel_flops * world) / (ms_max * 1e-3 / args.steps)
                                      / world / 1e12 / peak_nominal,
     }
+    restore_stdout()
     print(json.dumps(line), flush=True)
     if world > 1:
+        os.dup2(2, 1)
         dist.barrier()
         dist.destroy_process_group()
+        restore_stdout()
 
 
 def main():
