@@ -54,8 +54,14 @@ int run_blocks(const std::vector<Block>& blocks, F fn) {
     if (rc[k] != O2D_OK) msg[k] = o2d_last_error();   // the message is thread-local: carry it over
   };
   std::vector<std::thread> th;
-  for (int k = 1; k < nb; ++k) th.emplace_back(body, k);
+  int started = 1;
+  try {
+    for (int k = 1; k < nb; ++k) { th.emplace_back(body, k); ++started; }
+  } catch (...) {
+    // no more host threads to be had: the remaining blocks run on this thread, nothing crosses the C ABI
+  }
   body(0);
+  for (int k = started; k < nb; ++k) body(k);
   for (auto& t : th) t.join();
   for (int k = 0; k < nb; ++k)
     if (rc[k] != O2D_OK) return fail(rc[k], "device slot %d: %s", k, msg[k].c_str());
