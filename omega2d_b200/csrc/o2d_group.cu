@@ -125,6 +125,7 @@ extern "C" int o2d_group_points_on_points(o2d_group* g, int core, int results,
   if (blocks.size() <= 1)   // also the path that validates arguments for empty inputs
     return o2d_points_on_points(g->ctx[0], core, results, O2D_MEM_HOST, ns, sx, sy, ss, sr, nt, tx, ty, tr,
                                 tu, tv, tq, tux, tvx, tuy, tvy);
+  if (!tx || !ty || !tu || !tv) return fail(O2D_ERR_INVALID, "NULL target array");   // offsets below would hide a NULL
   return run_blocks(blocks, [&](int k, Block b) {
     return o2d_points_on_points(g->ctx[k], core, results, O2D_MEM_HOST, ns, sx, sy, ss, sr,
                                 b.n, tx + b.lo, ty + b.lo, at(tr, b.lo), at(tu, b.lo), at(tv, b.lo), at(tq, b.lo),
@@ -144,6 +145,7 @@ extern "C" int o2d_group_find_vels(o2d_group* g, int core, int results,
   if (blocks.size() <= 1)
     return o2d_find_vels(g->ctx[0], core, results, O2D_MEM_HOST, nv, vx, vy, vs, vr, np, nnodes, nx, ny, idx, pvs, pss,
                          nt, tx, ty, tr, tu, tv, tq, fsx, fsy);
+  if (!tx || !ty || !tu || !tv) return fail(O2D_ERR_INVALID, "NULL target array");
   return run_blocks(blocks, [&](int k, Block b) {
     return o2d_find_vels(g->ctx[k], core, results, O2D_MEM_HOST, nv, vx, vy, vs, vr, np, nnodes, nx, ny, idx, pvs, pss,
                          b.n, tx + b.lo, ty + b.lo, at(tr, b.lo), at(tu, b.lo), at(tv, b.lo), at(tq, b.lo), fsx, fsy);
@@ -157,6 +159,7 @@ extern "C" int o2d_group_panels_on_points(o2d_group* g, int np, int nnodes, cons
   const auto blocks = cut(nt, devices_for(g, 5.0 * (double)np * (double)nt));
   if (blocks.size() <= 1)
     return o2d_panels_on_points(g->ctx[0], O2D_MEM_HOST, np, nnodes, nx, ny, idx, vs, ss, nt, tx, ty, tu, tv);
+  if (!tx || !ty || !tu || !tv) return fail(O2D_ERR_INVALID, "NULL target array");
   return run_blocks(blocks, [&](int k, Block b) {
     return o2d_panels_on_points(g->ctx[k], O2D_MEM_HOST, np, nnodes, nx, ny, idx, vs, ss,
                                 b.n, tx + b.lo, ty + b.lo, tu + b.lo, tv + b.lo);
@@ -171,7 +174,7 @@ extern "C" int o2d_group_points_on_panels(o2d_group* g, int ns, const float* sx,
   const auto blocks = cut(ns, devices_for(g, 5.0 * (double)np * (double)ns));
   if (blocks.size() <= 1 || np <= 0)
     return o2d_points_on_panels(g->ctx[0], O2D_MEM_HOST, ns, sx, sy, ss, np, nnodes, nx, ny, idx, area, pu, pv);
-  if (!pu || !pv) return fail(O2D_ERR_INVALID, "NULL output array");
+  if (!pu || !pv || !sx || !sy || !ss) return fail(O2D_ERR_INVALID, "NULL source or output array");
   std::vector<float> part(2 * (size_t)np * blocks.size(), 0.0f);
   const int rc = run_blocks(blocks, [&](int k, Block b) {
     float* u = part.data() + 2 * (size_t)np * k;
