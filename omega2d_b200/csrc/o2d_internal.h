@@ -58,7 +58,7 @@ inline int res_ncomp(int res) {
   return 0;
 }
 inline int res_targets_per_thread(int res, bool fine = false) {
-  const int r = (res == 0 || res == 4) ? 4 : 2;
+  const int r = (res == 0 || res == 4) ? 4 : (res == 2 ? 2 : 3);   // mirrors ResTraits<RES>::R
   return fine ? r / 2 : r;
 }
 

@@ -34,9 +34,9 @@ namespace o2d {
 // how they map onto the reference's per-pair updates is in apply_outputs() below.
 template <int RES> struct ResTraits;
 template <> struct ResTraits<RES_U>    { static constexpr int NCOMP = 2; static constexpr int R = 4; static constexpr bool GRAD = false; };
-template <> struct ResTraits<RES_UW>   { static constexpr int NCOMP = 4; static constexpr int R = 2; static constexpr bool GRAD = true; };
+template <> struct ResTraits<RES_UW>   { static constexpr int NCOMP = 4; static constexpr int R = 3; static constexpr bool GRAD = true; };
 template <> struct ResTraits<RES_UE>   { static constexpr int NCOMP = 3; static constexpr int R = 2; static constexpr bool GRAD = true; };
-template <> struct ResTraits<RES_UG>   { static constexpr int NCOMP = 6; static constexpr int R = 2; static constexpr bool GRAD = true; };
+template <> struct ResTraits<RES_UG>   { static constexpr int NCOMP = 6; static constexpr int R = 3; static constexpr bool GRAD = true; };
 template <> struct ResTraits<RES_VORT> { static constexpr int NCOMP = 1; static constexpr int R = 4; static constexpr bool GRAD = false; };
 
 // Fold the float64 component sums of one target into the float outputs exactly like the
