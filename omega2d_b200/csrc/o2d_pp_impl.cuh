@@ -323,7 +323,9 @@ struct PPConfig {
   static constexpr int TILE = FINE ? kFineTile : kTile;
   static constexpr int R = FINE ? ResTraits<RES>::R / 2 : ResTraits<RES>::R;
   static constexpr size_t SMEM = 2 * (size_t)TILE * 16 + 64;
-  static auto kernel() { return pp_kernel<CORE, RES, THREADS, TILE, R>; }
+  // inner-loop unroll: 8 source pairs for the big configuration (4 for the branchy EXP core), 4 for the small tiles
+  static constexpr int UNROLL = (FINE || CORE == CORE_EXP) ? 4 : 8;
+  static auto kernel() { return pp_kernel<CORE, RES, THREADS, TILE, R, UNROLL>; }
 };
 
 template <int CORE, int RES, bool FINE>
