@@ -180,7 +180,7 @@ int o2d_advect(o2d_context* ctx, int core, int order, int mem,
 
 /*
  * `nsteps` consecutive o2d_advect steps with the particle state resident on the GPU in between: what
- * Simulation::step does nsteps times for an inviscid particle-only run (reference src/Simulation.cpp:611-742 with
+ * Simulation::step does nsteps times for an inviscid particle-only run (reference src/Simulation.cpp:687-744 with
  * "viscous": "none", e.g. examples/speedtest20kx10.json = 10 steps of 20 000 particles), with one upload before
  * the first and one download after the last step.  u,v hold what the last step leaves in them.
  */
