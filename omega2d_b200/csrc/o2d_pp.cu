@@ -1,6 +1,8 @@
 // o2d_pp.cu -- dispatch over cores, source packing, combine, Gaussian vorticity, elementwise helpers.
 #include "o2d_pp_impl.cuh"
 
+#include <atomic>
+
 namespace o2d {
 
 template <int CORE> cudaError_t launch_pp_core(int, const PPArgs&, int, cudaStream_t, bool);
@@ -30,10 +32,11 @@ cudaError_t launch_pp(int core, int res, const PPArgs& a, int nchunks, cudaStrea
 }
 
 int pp_occupancy(int core, int res, bool fine) {
-  static int cache[2][5][5] = {};
+  // filled lazily; several host threads (o2d_group) may race to fill a slot with the same value
+  static std::atomic<int> cache[2][5][5] = {};
   if (core < 0 || core > 4 || res < 0 || res > 4) return 1;
-  int& slot = cache[fine ? 1 : 0][core][res];
-  if (slot == 0) {
+  std::atomic<int>& slot = cache[fine ? 1 : 0][core][res];
+  if (slot.load(std::memory_order_relaxed) == 0) {
     int v = 1;
     if (res == RES_VORT) v = fine ? occupancy_one<CORE_RM, RES_VORT, true>() : occupancy_one<CORE_RM, RES_VORT, false>();
     else switch (core) {
@@ -43,9 +46,9 @@ int pp_occupancy(int core, int res, bool fine) {
       case CORE_V2:  v = pp_occupancy_core<CORE_V2>(res, fine); break;
       case CORE_V3:  v = pp_occupancy_core<CORE_V3>(res, fine); break;
     }
-    slot = v;
+    slot.store(v, std::memory_order_relaxed);
   }
-  return slot;
+  return slot.load(std::memory_order_relaxed);
 }
 
 cudaError_t launch_pp_combine(int res, const double* partial, int nchunks, int nt, const OutPtrs& out,
