@@ -3,6 +3,8 @@ GPU it fails loudly (no CPU fallback); its flop accounting equals the reference'
 import ctypes
 import re
 
+import numpy as np
+
 import pytest
 
 import omega2d_b200 as o2d
@@ -55,3 +57,25 @@ def test_default_core_is_the_references_default():
     lib = o2d.load_library()
     assert lib.o2d_get_default_core() == o2d.CORE_ID["v2"]   # reference src/CoreFunc.h:38
     assert lib.o2d_set_default_core(99) == o2d.ERR_INVALID
+
+
+def test_group_without_gpu_is_an_error_not_a_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(o2d.O2DError) as ei:
+        o2d.Group()
+    assert ei.value.code == o2d.ERR_NO_DEVICE
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 11, 12, 13, 1000, 12345])
+def test_vtu_size_query_matches_the_restated_writer(n, port):
+    """o2d_vtu_points_size is pure host logic (the XML skeleton + base64 lengths): it must equal the length of the file
+    the restated Points::write_vtk produces, for every combination of optional arrays."""
+    import itertools
+    a = np.zeros(n, np.float32)
+    for hs, hr, hw, he in itertools.product((0, 1), repeat=4):
+        img = port.vtu_points(0.5, a, a, a if hs else None, a if hr else None, a, a, w=a if hw else None, e=a if he else None)
+        assert len(img) == o2d.vtu_points_size(n, hs, hr, hw, he), (n, hs, hr, hw, he)
+    with pytest.raises(o2d.O2DError):
+        o2d.vtu_points_size(0)
