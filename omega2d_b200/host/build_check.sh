@@ -12,6 +12,9 @@ mkdir -p "$ROOT/build"
 g++ -std=c++17 -O2 -Wall -I"$HERE" "$ROOT/tests/cpp/test_find_vels.cpp" \
     -L"$ROOT/omega2d_b200" -lomega2d_b200 -Wl,-rpath,'$ORIGIN/../omega2d_b200' -o "$ROOT/build/test_find_vels"
 echo "built build/test_find_vels"
+g++ -std=c++17 -O2 -Wall -I"$HERE" "$ROOT/examples/speedtest20kx10.cpp" \
+    -L"$ROOT/omega2d_b200" -lomega2d_b200 -Wl,-rpath,'$ORIGIN/../omega2d_b200' -o "$ROOT/build/speedtest20kx10"
+echo "built build/speedtest20kx10"
 if [ -d "$REF/src" ]; then
   cat > "$ROOT/build/ref_containers_check.cpp" <<'CPP'
 // the reference's containers + this repository's influence header instead of Influence.h

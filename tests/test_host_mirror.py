@@ -110,3 +110,26 @@ def test_find_vels_cpp_vs_oracle(tmp_path, port):
     # .vtu files through the mirror (VtkB200.h -> o2d_write_vtu_points): byte-identical to the restated writer
     assert (tmp_path / "part_00_00007.vtu").read_bytes() == port.vtu_points(0.25, vx, vy, vs_, vr, wu, wv, w=ww)
     assert (tmp_path / "fldpt_01_00007.vtu").read_bytes() == port.vtu_points(0.25, fx, fy, None, None, np.zeros_like(fx), np.zeros_like(fx), w=fw)   # find_vort zeroed the velocities
+
+
+@pytest.mark.gpu
+def test_speedtest_example_program(tmp_path, port):
+    """examples/speedtest20kx10.cpp: the reference's timing scene (20k particles x 10 RK2 steps) through the mirror;
+    per-step and GPU-resident runs agree bit for bit and track the CPU restatement."""
+    exe = os.path.join(ROOT, "build", "speedtest20kx10")
+    if not os.path.exists(exe):
+        subprocess.run(["bash", os.path.join(ROOT, "omega2d_b200", "host", "build_check.sh")], check=True)
+    out = tmp_path / "st.bin"
+    res = subprocess.run([exe, str(out)], check=True, capture_output=True, text=True)
+    assert "agree bit for bit: yes" in res.stdout and "resident" in res.stdout, res.stdout
+    n = 20000
+    a = np.fromfile(out, np.float32).reshape(5, n)
+    x0, y0, x1, y1, s = a
+    assert np.abs(x0).max() <= 2.0 and np.abs(s).max() <= 1.0
+    r = np.full(n, np.float32(2.0 * np.sqrt(6.0) * np.sqrt(0.005 / 100.0)), np.float32)
+    wx, wy = x0, y0
+    for _ in range(10):
+        wx, wy, _, _ = port.advect("v2", 2, wx, wy, s, r, 0.005)
+    d = np.hypot(x1 - wx, y1 - wy)
+    assert np.percentile(d, 90) < 4e-5 and d.max() < 5e-3, (np.percentile(d, 90), d.max())
+    assert np.hypot(x1 - x0, y1 - y0).max() > 1e-3
