@@ -124,7 +124,7 @@ __device__ __forceinline__ void tile_sum(const float4* __restrict__ s, const flo
     const float2 nsx = f2(A.x, A.y), nsy = f2(A.z, A.w);
     const float2 str = f2(B.x, B.y);
     const float2 rho = (UNI && RES != RES_VORT) ? add2(f2(B.z, B.w), tau[0]) : f2(B.z, B.w);
-    if (CORE == CORE_EXP && RES != RES_VORT) {
+    if constexpr (CORE == CORE_EXP && RES != RES_VORT) {
       // compact-exponential core: ONE warp vote per source pair decides whether all R targets of all lanes are in
       // the reference's far branch (K = 1/d2); only the few source pairs that have a close target anywhere in the
       // warp go through core_eval's per-target test and general path
@@ -152,22 +152,22 @@ __device__ __forceinline__ void tile_sum(const float4* __restrict__ s, const flo
           pair_accumulate<RES, false>(part[k], str, K, Bb, dxk[k], dyk[k], d2);
         }
       }
-      continue;
-    }
+    } else {
 #pragma unroll
-    for (int k = 0; k < R; ++k) {
-      const float2 dx = add2(tx[k], nsx);
-      const float2 dy = add2(ty[k], nsy);
-      if (RES == RES_VORT) {
-        // src/InfluenceVort.h:109-114; str = 2 ss/sr^2, rho = log2(e)/sr^2
-        const float2 d2 = fma2(dy, dy, mul2(dx, dx));
-        const float2 arg = mul2(d2, rho);
-        const float2 e = make_float2(mufu_ex2(-arg.x), mufu_ex2(-arg.y));
-        part[k][0] = fma2(str, e, part[k][0]);
-      } else {
-        float2 K, Bb, d2;
-        core_eval<CORE, T::GRAD, UNI, RES != RES_UG>(dx, dy, rho, tau[k], K, Bb, d2, lim[k]);
-        pair_accumulate<RES, CoreTraits<CORE>::kBbDeferred>(part[k], str, K, Bb, dx, dy, d2);
+      for (int k = 0; k < R; ++k) {
+        const float2 dx = add2(tx[k], nsx);
+        const float2 dy = add2(ty[k], nsy);
+        if (RES == RES_VORT) {
+          // src/InfluenceVort.h:109-114; str = 2 ss/sr^2, rho = log2(e)/sr^2
+          const float2 d2 = fma2(dy, dy, mul2(dx, dx));
+          const float2 arg = mul2(d2, rho);
+          const float2 e = make_float2(mufu_ex2(-arg.x), mufu_ex2(-arg.y));
+          part[k][0] = fma2(str, e, part[k][0]);
+        } else {
+          float2 K, Bb, d2;
+          core_eval<CORE, T::GRAD, UNI, RES != RES_UG>(dx, dy, rho, tau[k], K, Bb, d2, lim[k]);
+          pair_accumulate<RES, CoreTraits<CORE>::kBbDeferred>(part[k], str, K, Bb, dx, dy, d2);
+        }
       }
     }
   }

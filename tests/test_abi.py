@@ -79,3 +79,22 @@ def test_vtu_size_query_matches_the_restated_writer(n, port):
         assert len(img) == o2d.vtu_points_size(n, hs, hr, hw, he), (n, hs, hr, hw, he)
     with pytest.raises(o2d.O2DError):
         o2d.vtu_points_size(0)
+
+
+def test_cmake_build_exports_the_same_abi(tmp_path):
+    """omega2d_b200/CMakeLists.txt (what a CMake host project such as Omega2D adds with add_subdirectory) builds the same
+    library: every function the header declares is exported.  nvcc cross-compiles sm_100a without a GPU."""
+    import os
+    import shutil
+    import subprocess
+    if not (shutil.which("cmake") and shutil.which("ninja") and os.path.exists("/usr/local/cuda/bin/nvcc")):
+        pytest.skip("cmake / ninja / nvcc not available")
+    src = os.path.join(os.path.dirname(o2d.HEADER_PATH), "..", "omega2d_b200")
+    cfg = subprocess.run(["cmake", "-G", "Ninja", "-DCMAKE_CUDA_COMPILER=/usr/local/cuda/bin/nvcc", "-DCMAKE_CUDA_HOST_COMPILER=/usr/bin/g++",
+                          "-DCMAKE_CXX_COMPILER=/usr/bin/g++", "-S", src, "-B", str(tmp_path)], capture_output=True, text=True)
+    assert cfg.returncode == 0, cfg.stdout[-2000:] + cfg.stderr[-2000:]
+    bld = subprocess.run(["ninja", "-C", str(tmp_path)], capture_output=True, text=True)
+    assert bld.returncode == 0, bld.stdout[-3000:]
+    lib = ctypes.CDLL(str(tmp_path / "libomega2d_b200.so"))
+    for n in declared_functions():
+        assert hasattr(lib, n), n
