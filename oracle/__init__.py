@@ -65,6 +65,13 @@ def build_ref(reference: str = "/root/reference") -> bool:
             not os.path.exists(ref_path(c)) or os.path.getmtime(ref_path(c)) < os.path.getmtime(drv)
             for c in CORES
         )
+        # the drop-in binary (reference containers + this repository's influence headers) follows its sources
+        dropin = os.path.join(HERE, "_ref", "ref_dropin_v2")
+        root = os.path.dirname(HERE)
+        deps = [os.path.join(root, "tests", "cpp", "ref_dropin.cpp")] + \
+               [os.path.join(root, "omega2d_b200", "host", f) for f in os.listdir(os.path.join(root, "omega2d_b200", "host")) if f.endswith(".h")]
+        if os.path.exists(os.path.join(root, "omega2d_b200", "libomega2d_b200.so")):
+            stale = stale or not os.path.exists(dropin) or any(os.path.getmtime(dropin) < os.path.getmtime(d) for d in deps)
         if stale:
             env = dict(os.environ, O2D_REFERENCE=reference)
             subprocess.run([os.path.join(HERE, "build_ref.sh")], check=True, env=env)

@@ -18,6 +18,7 @@ set -euo pipefail
 REF="${O2D_REFERENCE:-/root/reference}"
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 OUT="$HERE/_ref"
+ROOT="$(cd "$HERE/.." && pwd)"
 if [ ! -d "$REF/src" ]; then
   echo "build_ref.sh: $REF/src not found; keeping prebuilt oracle/_ref as is" >&2
   exit 0
@@ -51,6 +52,16 @@ build_core () {
       -shared -o "$OUT/libo2dref_${name}.so" \
       "$HERE/ref_driver.cpp" "$d/Body.cpp" "$STAGE/tinyexpr.o" "$STAGE/tinyxml2.o"
   echo "built $OUT/libo2dref_${name}.so"
+  # the drop-in check (tests/cpp/ref_dropin.cpp): the reference's OWN containers with this repository's influence headers
+  # in place of Influence.h, linked against the product library, compared inside the program with the reference's CPU
+  # loops from the library just built.  Default core only (V2), like an unmodified Omega2D build.
+  if [ "$name" = "v2" ] && [ -f "$ROOT/omega2d_b200/libomega2d_b200.so" ]; then
+    g++ -std=c++17 -O2 $MARCH -fopenmp -DVERBOSE=false -w -I"$d" -I"$REF/lib" -I"$REF/lib/tinyexpr" -I"$REF/lib/tinyxml2" \
+        -I"$ROOT/omega2d_b200/host" "$ROOT/tests/cpp/ref_dropin.cpp" "$d/Body.cpp" "$STAGE/tinyexpr.o" "$STAGE/tinyxml2.o" \
+        -L"$OUT" -lo2dref_v2 -L"$ROOT/omega2d_b200" -lomega2d_b200 \
+        -Wl,-rpath,'$ORIGIN' -Wl,-rpath,'$ORIGIN/../../omega2d_b200' -o "$OUT/ref_dropin_v2"
+    echo "built $OUT/ref_dropin_v2"
+  fi
 }
 
 pids=()

@@ -1,0 +1,140 @@
+// tests/cpp/ref_dropin.cpp -- TEST INFRASTRUCTURE.  The drop-in claim end to end:
+//   * the containers are the REFERENCE's own Points<float> / Surfaces<float> / Collection, built from ElementPackets the
+//     way Simulation::add_elements builds them (reference src/Simulation.cpp:826-912);
+//   * the influence layer is this repository's InfluenceB200.h / ConvectionB200.h in place of the reference's
+//     Influence.h / InfluenceVort.h (the include swap of INTEGRATION.md section 2), so find_vels / find_vort run on
+//     the GPU through the C ABI;
+//   * the answer is checked against the reference's own CPU loops on the same inputs, taken from
+//     oracle/_ref/libo2dref_v2.so (built -Bsymbolic: its calls bind to its own template instantiations, not to the
+//     identically named ones this program defines).
+// Built only where /root/reference exists (oracle/build_ref.sh -> oracle/_ref/ref_dropin_v2); run on the GPU box by
+// tests/test_host_mirror.py.  Prints one line per check and exits non-zero on a mismatch.
+#include "Collection.h"
+#include "ResultsType.h"
+#include "ExecEnv.h"
+#define OMEGA2D_REFERENCE_HEADERS
+#include "InfluenceB200.h"
+#include "ConvectionB200.h"
+#include "ReflectB200.h"
+#include "VtkB200.h"
+
+#include <cmath>
+#include <cstdio>
+#include <random>
+#include <vector>
+
+extern "C" {
+int o2dref_core_id();
+int o2dref_find_vels(int results, int nv, const float* vx, const float* vy, const float* vs, const float* vr,
+                     int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                     const float* pvs, const float* pss, int nt, const float* tx, const float* ty, const float* tr,
+                     float* tu, float* tv, float* tq, double fsx, double fsy);
+int o2dref_points_vorticity(int ns, const float* sx, const float* sy, const float* ss, const float* sr,
+                            int nt, const float* tx, const float* ty, float* tw);
+int o2dref_clear_inner_layer(int method, int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                             int n, float* x, float* y, float* s, const float* r, float cutoff_factor, float ips);
+}
+
+static double rel_err(const std::vector<float>& gu, const std::vector<float>& gv,
+                      const std::vector<float>& wu, const std::vector<float>& wv) {
+  double num = 0.0, den = 0.0;
+  for (size_t i = 0; i < gu.size(); ++i) {
+    num = std::max(num, std::hypot((double)gu[i] - wu[i], (double)gv[i] - wv[i]));
+    den = std::max(den, std::hypot((double)wu[i], (double)wv[i]));
+  }
+  return num / den;
+}
+
+int main() {
+  if (o2dref_core_id() != 3 || o2d_host::selected_core() != O2D_CORE_V2) { std::puts("core mismatch"); return 2; }
+  const size_t nv = 6000, np = 143, nf = 700;
+  const float vdelta = 0.043818f;
+  const std::array<double,Dimensions> fs = {1.0, 0.0};
+  std::mt19937 gen(7);
+  std::uniform_real_distribution<float> U(0.0f, 1.0f);
+
+  // vortex particles in an annulus around a unit-diameter circle; field points above it; the circle as panels
+  std::vector<float> vx(nv), vy(nv), vs(nv), vr(nv, vdelta), px(2 * nv);
+  for (size_t i = 0; i < nv; ++i) {
+    const float rho = 0.55f + 0.9f * U(gen), th = 6.2831853f * U(gen);
+    vx[i] = rho * std::cos(th); vy[i] = rho * std::sin(th); vs[i] = (U(gen) - 0.5f) * 2e-3f;
+    px[2*i] = vx[i]; px[2*i+1] = vy[i];
+  }
+  std::vector<float> fx(nf), fy(nf), pf(2 * nf);
+  for (size_t i = 0; i < nf; ++i) { fx[i] = -1.5f + 3.0f * U(gen); fy[i] = 0.8f + U(gen); pf[2*i] = fx[i]; pf[2*i+1] = fy[i]; }
+  std::vector<float> nx(np), ny(np), pvs(np), pss(np), pn(2 * np), pval(2 * np);
+  std::vector<Int> idx(2 * np);
+  for (size_t i = 0; i < np; ++i) {
+    const float th = -6.2831853f * (float)i / (float)np;
+    nx[i] = 0.5f * std::cos(th); ny[i] = 0.5f * std::sin(th);
+    pvs[i] = 2.0f * std::sin(th) + 0.1f; pss[i] = 0.3f * std::cos(th);
+    pn[2*i] = nx[i]; pn[2*i+1] = ny[i]; pval[2*i] = pvs[i]; pval[2*i+1] = pss[i];
+    idx[2*i] = (Int)i; idx[2*i+1] = (Int)((i + 1) % np);
+  }
+  // the reference's constructors (src/Points.h:51-112, src/Surfaces.h:57-170)
+  std::vector<Collection> vort, bdry, fldpt;
+  vort.push_back(Points<float>(ElementPacket<float>(px, std::vector<Int>(), vs, nv, 0), active, lagrangian, nullptr, vdelta));
+  bdry.push_back(Surfaces<float>(ElementPacket<float>(pn, idx, pval, np, 1), active, fixed, nullptr));
+  fldpt.push_back(Points<float>(ElementPacket<float>(pf, std::vector<Int>(), std::vector<float>(), nf, 0), inert, lagrangian, nullptr, 0.0f));   // tracers: find_vels skips collections that do not move
+
+  int bad = 0;
+  auto check = [&](const char* what, double err, double tol) {
+    std::printf("  %-58s max rel err %.2e (tolerance %.0e) %s\n", what, err, tol, err < tol ? "ok" : "MISMATCH");
+    if (!(err < tol)) ++bad;
+  };
+
+  // Convection::find_vels on the particles and on the field points (reference containers, GPU influence layer)
+  find_vels<float,double>(fs, vort, bdry, vort);
+  find_vels<float,double>(fs, vort, bdry, fldpt);
+  {
+    std::vector<float> wu(nv), wv(nv);
+    o2dref_find_vels(velonly, (int)nv, vx.data(), vy.data(), vs.data(), vr.data(), (int)np, (int)np, nx.data(), ny.data(),
+                     idx.data(), pvs.data(), pss.data(), (int)nv, vx.data(), vy.data(), vr.data(), wu.data(), wv.data(), nullptr, fs[0], fs[1]);
+    const auto& u = std::get<Points<float>>(vort[0]).get_vel();
+    check("find_vels: particles + panels on the particles", rel_err(u[0], u[1], wu, wv), 1e-5);
+    std::vector<float> fu(nf), fv(nf);
+    o2dref_find_vels(velonly, (int)nv, vx.data(), vy.data(), vs.data(), vr.data(), (int)np, (int)np, nx.data(), ny.data(),
+                     idx.data(), pvs.data(), pss.data(), (int)nf, fx.data(), fy.data(), nullptr, fu.data(), fv.data(), nullptr, fs[0], fs[1]);
+    const auto& uf = std::get<Points<float>>(fldpt[0]).get_vel();
+    check("find_vels: particles + panels on inert field points", rel_err(uf[0], uf[1], fu, fv), 1e-5);
+  }
+  // velocity + vorticity, forced like write_vtk does (src/Simulation.cpp:408-414)
+  find_vels<float,double>(fs, vort, bdry, vort, velandvort, true);
+  {
+    std::vector<float> wu(nv), wv(nv), ww(nv), zero(nv, 0.0f);
+    o2dref_find_vels(velandvort, (int)nv, vx.data(), vy.data(), vs.data(), vr.data(), (int)np, (int)np, nx.data(), ny.data(),
+                     idx.data(), pvs.data(), pss.data(), (int)nv, vx.data(), vy.data(), vr.data(), wu.data(), wv.data(), ww.data(), fs[0], fs[1]);
+    const Points<float>& p = std::get<Points<float>>(vort[0]);
+    check("find_vels(velandvort): velocity", rel_err(p.get_vel()[0], p.get_vel()[1], wu, wv), 1e-5);
+    check("find_vels(velandvort): vorticity", rel_err(p.get_vort(), zero, ww, zero), 1e-5);
+  }
+  // find_vort: Gaussian vorticity on the field points, then 1/(2 pi)
+  find_vort<float,double>(vort, bdry, fldpt);
+  {
+    std::vector<float> ww(nf, 0.0f), zero(nf, 0.0f);
+    o2dref_points_vorticity((int)nv, vx.data(), vy.data(), vs.data(), vr.data(), (int)nf, fx.data(), fy.data(), ww.data());
+    for (auto& w : ww) w = (float)(w * (0.5 / M_PI));
+    check("find_vort on the field points", rel_err(std::get<Points<float>>(fldpt[0]).get_vort(), zero, ww, zero), 1e-5);
+  }
+  // clear_inner_layer (push) on a copy of the particles pulled towards the body
+  {
+    std::vector<float> qx(vx), qy(vy), qs(vs), qr(vr), pq(2 * nv);
+    for (size_t i = 0; i < nv; ++i) { qx[i] *= 0.9f; qy[i] *= 0.9f; pq[2*i] = qx[i]; pq[2*i+1] = qy[i]; }
+    std::vector<Collection> near;
+    near.push_back(Points<float>(ElementPacket<float>(pq, std::vector<Int>(), vs, nv, 0), active, lagrangian, nullptr, vdelta));
+    const float cutoff = 0.5f / std::sqrt(2.0f * 3.14159265f), ips = 0.02191f;
+    clear_inner_layer<float>(1, bdry, near, cutoff, ips);
+    o2dref_clear_inner_layer(1, (int)np, (int)np, nx.data(), ny.data(), idx.data(), (int)nv, qx.data(), qy.data(), qs.data(), qr.data(), cutoff, ips);
+    const auto& x = std::get<Points<float>>(near[0]).get_pos();
+    double d = 0.0; size_t moved = 0;
+    for (size_t i = 0; i < nv; ++i) {
+      d = std::max(d, std::hypot((double)x[0][i] - qx[i], (double)x[1][i] - qy[i]));
+      moved += (x[0][i] != pq[2*i] || x[1][i] != pq[2*i+1]);
+    }
+    std::printf("  clear_inner_layer moved %zu particles\n", moved);
+    check("clear_inner_layer (push): max |dx| against the reference", d, 1e-5);
+    if (moved < 10) ++bad;
+  }
+  std::printf("ref_dropin: %s\n", bad ? "FAILED" : "all checks passed");
+  return bad ? 1 : 0;
+}

@@ -133,3 +133,16 @@ def test_speedtest_example_program(tmp_path, port):
     d = np.hypot(x1 - wx, y1 - wy)
     assert np.percentile(d, 90) < 4e-5 and d.max() < 5e-3, (np.percentile(d, 90), d.max())
     assert np.hypot(x1 - x0, y1 - y0).max() > 1e-3
+
+
+@pytest.mark.gpu
+def test_reference_containers_with_the_b200_influence_layer():
+    """oracle/_ref/ref_dropin_v2 (tests/cpp/ref_dropin.cpp, built where the reference tree exists): the REFERENCE's own
+    Points / Surfaces / Collection objects, this repository's InfluenceB200.h / ConvectionB200.h / ReflectB200.h in place
+    of the reference's headers, results compared inside the program with the reference's own CPU loops."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_dropin_v2")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_dropin_v2 was not built (needs the reference tree at build time)")
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "all checks passed" in res.stdout, res.stdout + res.stderr
+    assert res.stdout.count(" ok") >= 6, res.stdout
