@@ -16,10 +16,15 @@
 #include "InfluenceB200.h"
 #include "ConvectionB200.h"
 #include "ReflectB200.h"
+#include "CoefficientsB200.h"
 #include "VtkB200.h"
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iterator>
+#include <unistd.h>
 #include <random>
 #include <vector>
 
@@ -31,6 +36,10 @@ int o2dref_find_vels(int results, int nv, const float* vx, const float* vy, cons
                      float* tu, float* tv, float* tq, double fsx, double fsy);
 int o2dref_points_vorticity(int ns, const float* sx, const float* sy, const float* ss, const float* sr,
                             int nt, const float* tx, const float* ty, float* tw);
+int o2dref_panels_on_panels_coeff(int nsrc, int nsnodes, const float* snx, const float* sny, const uint32_t* sidx,
+                                  int ntarg, int ntnodes, const float* tnx, const float* tny, const uint32_t* tidx,
+                                  int same, float* coeffs, float* tt_x, float* tt_y, float* tn_x, float* tn_y,
+                                  float* tarea, float* sarea);
 int o2dref_clear_inner_layer(int method, int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
                              int n, float* x, float* y, float* s, const float* r, float cutoff_factor, float ips);
 }
@@ -134,6 +143,38 @@ int main() {
     std::printf("  clear_inner_layer moved %zu particles\n", moved);
     check("clear_inner_layer (push): max |dx| against the reference", d, 1e-5);
     if (moved < 10) ++bad;
+  }
+  // BEM influence-coefficient block of the body on itself: CoefficientVisitor on the reference's Surfaces
+  {
+    Vector<float> c = std::visit(CoefficientVisitor<float>(), bdry[0], bdry[0]);
+    std::vector<float> want(4 * np * np), t1(np), t2(np), t3(np), t4(np), t5(np), t6(np);
+    o2dref_panels_on_panels_coeff((int)np, (int)np, nx.data(), ny.data(), idx.data(), (int)np, (int)np, nx.data(), ny.data(), idx.data(),
+                                  1, want.data(), t1.data(), t2.data(), t3.data(), t4.data(), t5.data(), t6.data());
+    double num = 0.0, den = 0.0;
+    if (c.size() == want.size())
+      for (size_t k = 0; k < want.size(); ++k) { num = std::max(num, std::fabs((double)c[k] - want[k])); den = std::max(den, std::fabs((double)want[k])); }
+    else { num = 1.0; den = 1.0; }
+    check("panels_on_panels_coeff through CoefficientVisitor", num / den, 1e-5);
+  }
+  // Points::write_vtk: the reference's own member (CPU) and write_vtk_points (GPU) on the same reference object
+  {
+    char tmpl[] = "/tmp/o2d_dropin_XXXXXX";
+    const char* dir = mkdtemp(tmpl);
+    char cwd[4096];
+    if (dir && getcwd(cwd, sizeof(cwd)) && chdir(dir) == 0) {
+      Points<float>& p = std::get<Points<float>>(vort[0]);
+      const std::string a = p.write_vtk(0, 7, 0.25);                  // reference: VtkXmlWriter + cppcodec + tinyxml2
+      const std::string b = write_vtk_points(p, 0, 8, 0.25);          // this repository: one kernel + skeleton
+      auto slurp = [](const std::string& f) { std::ifstream s(f, std::ios::binary); return std::string(std::istreambuf_iterator<char>(s), {}); };
+      const std::string fa = slurp(a), fb = slurp(b);
+      const bool same = !fa.empty() && fa == fb;
+      std::printf("  write_vtk: reference %s (%zu bytes), GPU %s (%zu bytes): %s\n", a.c_str(), fa.size(), b.c_str(), fb.size(),
+                  same ? "identical ok" : "DIFFERENT");
+      if (!same) ++bad;
+      std::remove(a.c_str()); std::remove(b.c_str());
+      if (chdir(cwd) != 0) ++bad;
+      rmdir(dir);
+    } else { std::puts("  write_vtk: no temporary directory"); ++bad; }
   }
   std::printf("ref_dropin: %s\n", bad ? "FAILED" : "all checks passed");
   return bad ? 1 : 0;
