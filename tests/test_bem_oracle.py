@@ -8,8 +8,6 @@ import os
 import numpy as np
 import pytest
 
-import oracle
-
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 

@@ -1,7 +1,5 @@
 """GPU: o2d_vtu_points / o2d_write_vtu_points against the reference-written golden .vtu files and the restated writer,
 byte for byte; size-independent decode-back check at 1M particles."""
-import os
-
 import numpy as np
 import pytest
 

@@ -97,7 +97,6 @@ def test_find_vels_cpp_vs_oracle(tmp_path, port):
     nbc = (0.01 * (np.arange(npan) % 7)).astype(np.float32)
     np.testing.assert_allclose(rhs, port.vels_to_rhs_panels(nx, ny, idx, bu, bv, nbc), atol=2e-6)
     # clear_inner_layer through the mirror (ReflectB200.h -> o2d_clear_inner_layer)
-    import math
     qx, qy, ox, oy = arrs[31:35]
     want = port.clear_inner_layer(nx, ny, idx, qx, qy, np.float32(0.5) / np.sqrt(np.float32(2.0) * np.float32(3.14159265)), 0.02191)
     assert want[2] > 10

@@ -3,7 +3,7 @@
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import numpy as np, torch
+import torch
 import omega2d_b200 as o2d, oracle
 from omega2d_b200 import workloads as W
 core = sys.argv[1]; results = int(sys.argv[2]); n = int(sys.argv[3]); uniform = len(sys.argv) > 4

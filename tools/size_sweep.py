@@ -2,7 +2,7 @@
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import numpy as np, torch
+import torch
 import omega2d_b200 as o2d
 from omega2d_b200 import workloads as W
 ctx = o2d.Context(0)
