@@ -68,10 +68,12 @@ def build_ref(reference: str = "/root/reference") -> bool:
         # the drop-in binary (reference containers + this repository's influence headers) follows its sources
         dropin = os.path.join(HERE, "_ref", "ref_dropin_v2")
         root = os.path.dirname(HERE)
-        deps = [os.path.join(root, "tests", "cpp", "ref_dropin.cpp")] + \
+        seam = os.path.join(HERE, "_ref", "ref_external_seam_v2")
+        deps = [os.path.join(root, "tests", "cpp", "ref_dropin.cpp"), os.path.join(root, "tests", "cpp", "ref_external_seam.cpp")] + \
                [os.path.join(root, "omega2d_b200", "host", f) for f in os.listdir(os.path.join(root, "omega2d_b200", "host")) if f.endswith(".h")]
         if os.path.exists(os.path.join(root, "omega2d_b200", "libomega2d_b200.so")):
-            stale = stale or not os.path.exists(dropin) or any(os.path.getmtime(dropin) < os.path.getmtime(d) for d in deps)
+            stale = stale or not os.path.exists(dropin) or not os.path.exists(seam) or \
+                any(min(os.path.getmtime(dropin), os.path.getmtime(seam)) < os.path.getmtime(d) for d in deps)
         if stale:
             env = dict(os.environ, O2D_REFERENCE=reference)
             subprocess.run([os.path.join(HERE, "build_ref.sh")], check=True, env=env)

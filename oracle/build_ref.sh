@@ -61,6 +61,13 @@ build_core () {
         -L"$OUT" -lo2dref_v2 -L"$ROOT/omega2d_b200" -lomega2d_b200 \
         -Wl,-rpath,'$ORIGIN' -Wl,-rpath,'$ORIGIN/../../omega2d_b200' -o "$OUT/ref_dropin_v2"
     echo "built $OUT/ref_dropin_v2"
+    # the zero-source-change route: the reference's UNMODIFIED Influence.h with -DEXTERNAL_VEL_SOLVE, its two plugin
+    # symbols resolved from the product library (tests/cpp/ref_external_seam.cpp)
+    g++ -std=c++17 -O2 $MARCH -fopenmp -DVERBOSE=false -DEXTERNAL_VEL_SOLVE -w -I"$d" -I"$REF/lib" -I"$REF/lib/tinyexpr" -I"$REF/lib/tinyxml2" \
+        "$ROOT/tests/cpp/ref_external_seam.cpp" "$d/Body.cpp" "$STAGE/tinyexpr.o" "$STAGE/tinyxml2.o" \
+        -L"$OUT" -lo2dref_v2 -L"$ROOT/omega2d_b200" -lomega2d_b200 \
+        -Wl,-rpath,'$ORIGIN' -Wl,-rpath,'$ORIGIN/../../omega2d_b200' -o "$OUT/ref_external_seam_v2"
+    echo "built $OUT/ref_external_seam_v2"
   fi
 }
 

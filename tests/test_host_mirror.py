@@ -145,3 +145,16 @@ def test_reference_containers_with_the_b200_influence_layer():
     res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0 and "all checks passed" in res.stdout, res.stdout + res.stderr
     assert res.stdout.count(" ok") >= 8, res.stdout          # 6 influence checks, the BEM block, the .vtu file
+
+
+@pytest.mark.gpu
+def test_reference_external_seam_calls_the_library():
+    """oracle/_ref/ref_external_seam_v2 (tests/cpp/ref_external_seam.cpp): the reference's UNMODIFIED Influence.h built
+    with -DEXTERNAL_VEL_SOLVE; its points_affect_points leaves through external_vel_solver_f_ / _tr_f_, resolved from
+    libomega2d_b200.so, and must agree with the reference's own internal CPU loop."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_external_seam_v2")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_external_seam_v2 was not built (needs the reference tree at build time)")
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "all checks passed" in res.stdout, res.stdout + res.stderr
+    assert "external_vel_solver_tr_f_" in res.stdout and "external_vel_solver_f_ " in res.stdout
