@@ -18,7 +18,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-LIB_PATH = os.path.join(HERE, "libomega2d_b200.so")
+# O2D_LIB: load another build of the same library (A/B timing of two builds; development only)
+LIB_PATH = os.environ.get("O2D_LIB") or os.path.join(HERE, "libomega2d_b200.so")
 HEADER_PATH = os.path.join(ROOT, "include", "omega2d_b200.h")
 
 CORES = ("rm", "exp", "wl", "v2", "v3")

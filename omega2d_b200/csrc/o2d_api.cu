@@ -118,9 +118,6 @@ extern "C" int o2d_create(o2d_context** out, int device) {
   cudaDeviceGetAttribute(&c->sm_clock_khz, cudaDevAttrClockRate, device);
   CU(cudaSetDevice(device));
   CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
-  CU(cudaEventCreateWithFlags(&c->ev_gather, cudaEventDisableTiming));
-  CU(cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming));
   c->stream = c->own_stream;
   // pinned staging for small host arrays (see o2d_h2d_bytes); without it every copy takes the pageable path
   void* pin = nullptr;
@@ -147,10 +144,7 @@ extern "C" int o2d_destroy(o2d_context* c) {
   if (c->pin) cudaFreeHost(c->pin);
   for (auto& pr : c->ev_pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (auto& pr : c->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
-  cudaEventDestroy(c->ev_gather);
-  cudaEventDestroy(c->ev_pack);
   cudaStreamDestroy(c->own_stream);
-  cudaStreamDestroy(c->comm_stream);
   delete c;
   return O2D_OK;
 }
@@ -202,30 +196,74 @@ int o2d_res_from_results(int results) {
   return -1;
 }
 
-// one pair-sum launch over logical tiles [tile_begin, tile_end) of an already packed source array,
-// split into `nchunks` chunks (nchunks > 1 requires a partials buffer)
-static int pp_run_packed(o2d_context* c, int core, int res, const float4* packed,
-                         int tile_begin, int tile_end, int skip_begin, int skip_len,
-                         const float* tx, const float* ty, const float* tr, int nt, const OutPtrs& out,
-                         int* chunk_cursor, int nchunks, double* partial_base, bool fine = false) {
-  const int ntiles = tile_end - tile_begin;
-  if (ntiles <= 0 || nt <= 0 || nchunks <= 0) return O2D_OK;
-  if (nchunks > 1 && partial_base == nullptr) return fail(O2D_ERR_INVALID, "internal: chunked launch without partials");
+// ---- pair-sum launch plan ----------------------------------------------------------------------------------
+// The (target block, source tile) steps of an evaluation, in block-major order, are cut into equal contiguous runs,
+// one CTA each (PPArgs, o2d_internal.h).
+//  * Kernels that run as ONE 512-thread CTA per SM get one run per SM.  Every SM has the same work, so there is no
+//    last wave and no tail whatever the particle count, and only the two ends of a run touch the partial-sum buffer.
+//  * Kernels with several CTAs per SM (the 24-warp shapes, and the "fine" configuration) get kRunsPerSlot short runs
+//    per resident-CTA slot, placed by the hardware block scheduler.  Equal static runs do NOT work there: the warp
+//    schedulers favour some resident CTAs over others (measured with three 256-thread CTAs per SM and one equal run
+//    each: the three CTAs of an SM finished after 196, 240 and 323 ms; profiles/r02_pp_shape_search.md), whereas
+//    the warps of ONE CTA are held together by the four-stage tile window.  The CTAs left on a draining SM speed up,
+//    so the end-of-launch loss is ~1/10 of a run, not 1/2: 16 runs per slot cost ~0.5 %.
+//  * "fine" configuration (128 threads, 128*R targets x 256 sources per step) when the coarse steps are too few to
+//    give every SM a run worth starting (a few thousand to ~50 000 particles).
+// O2D_PP_RUNS_PER_SLOT, O2D_PP_MIN_STEPS and O2D_PP_FINE_BELOW override the constants (tuning only).
+struct PPPlan {
+  bool fine;
+  int ntiles, nblocks, nctas;
+  long long steps_per_cta;
+};
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e && *e ? atoi(e) : dflt;
+}
+static PPPlan pp_plan(o2d_context* c, int core, int res, long long ns_padded, int nt) {
+  static const int kRunsPerSlot = std::max(1, env_int("O2D_PP_RUNS_PER_SLOT", 16));
+  static const int kMinSteps = std::max(1, env_int("O2D_PP_MIN_STEPS", 2));
+  static const int kFineBelow = std::max(0, env_int("O2D_PP_FINE_BELOW", 16));
+  PPPlan p;
+  const int btb = pp_block_targets(core, res, false);
+  const long long big_steps = (long long)((nt + btb - 1) / btb) * (ns_padded / kBigTile);
+  p.fine = big_steps < (long long)kFineBelow * c->sm_count;
+  const int tile = p.fine ? kFineTile : kBigTile;
+  const int bt = pp_block_targets(core, res, p.fine);
+  p.ntiles = (int)(ns_padded / tile);
+  p.nblocks = (nt + bt - 1) / bt;
+  const long long total = (long long)p.nblocks * p.ntiles;
+  const int occ = pp_occupancy(core, res, p.fine);
+  const long long runs = (long long)c->sm_count * occ * (occ > 1 ? kRunsPerSlot : 1);
+  p.steps_per_cta = std::max<long long>((total + runs - 1) / runs, occ > 1 ? std::min<long long>(kMinSteps, p.ntiles) : 1);
+  p.nctas = (int)((total + p.steps_per_cta - 1) / p.steps_per_cta);
+  return p;
+}
+
+// the pair sums of every tile of an already packed source array (ns_padded sources, a multiple of kTile) onto nt targets
+static int pp_run_packed(o2d_context* c, int core, int res, const float4* packed, long long ns_padded,
+                         const float* tx, const float* ty, const float* tr, int nt, const OutPtrs& out) {
+  if (ns_padded <= 0 || nt <= 0) return O2D_OK;
+  const PPPlan p = pp_plan(c, core, res, ns_padded, nt);
   PPArgs a;
   a.packed = packed;
-  a.tile_begin = tile_begin;
-  a.tile_end = tile_end;
-  a.skip_begin = skip_begin;
-  a.skip_len = skip_len;
+  a.ntiles = p.ntiles;
+  a.nblocks = p.nblocks;
+  a.steps_per_cta = p.steps_per_cta;
   a.tx = tx; a.ty = ty; a.tr = tr; a.nt = nt;
   a.out = out;
-  a.partial = partial_base;
-  a.chunk_offset = chunk_cursor ? *chunk_cursor : 0;
-  a.tiles_per_chunk = (ntiles + nchunks - 1) / nchunks;
-  CU(launch_pp(core, res, a, nchunks, c->stream, fine));
-  c->launches++;
-  c->pair_launches++;
-  if (chunk_cursor) *chunk_cursor += nchunks;
+  const bool cut = p.steps_per_cta % p.ntiles != 0;   // some blocks are shared between CTAs
+  CU(c->partial.reserve((size_t)p.nctas * 2 * res_ncomp(res) * pp_block_targets(core, res, p.fine) * sizeof(double)));
+  a.partial = c->partial.as<double>();
+  {
+    PairTimer timer(c);
+    CU(launch_pp(core, res, a, p.nctas, c->stream, p.fine));
+    c->launches++;
+    c->pair_launches++;
+  }
+  if (cut) {
+    CU(launch_pp_combine(core, res, a, c->stream, p.fine));
+    c->launches++;
+  }
   return O2D_OK;
 }
 
@@ -237,38 +275,7 @@ int o2d_pp_device(o2d_context* c, int core, int res,
   CU(c->packed.reserve((size_t)ns_padded * 16));
   CU(launch_pack_sources(res == RES_VORT ? 100 : core, ns, sx, sy, ss, sr, c->packed.as<float4>(), ns_padded, c->stream));
   c->launches++;
-  // Small and medium problems: with the big configuration (256*R targets x 1024 sources per CTA-tile, ~33 us
-  // of work) a few thousand particles occupy a handful of SMs for one long tile, and up to ~200k particles the
-  // coarse units leave the last wave of CTAs uneven.  The fine configuration (128*R/2 targets x 256 sources)
-  // has the same per-SM rate for the velocity kernels (measured 12.86 vs 12.83 pairs/clk/SM at 1M, RM) and
-  // 32x smaller units: 5k particles 58 -> 17 us, 50k 10.7 -> 12.2 pairs/clk/SM, 200k 12.5 -> 12.7.  Above that
-  // the big one is kept (fewer barriers and LDS per pair; V2 with uniform radii: 12.7 vs 12.4).
-  const int Rb = res_targets_per_thread(res);
-  const long long big_units = (long long)((nt + kThreads * Rb - 1) / (kThreads * Rb)) * ((ns + kTile - 1) / kTile);
-  const bool fine = big_units < 96LL * c->sm_count * pp_occupancy(core, res);
-  const int tile = fine ? kFineTile : kTile;
-  const int threads = fine ? kFineThreads : kThreads;
-  const int R = res_targets_per_thread(res, fine);
-  const int ntiles = (ns + tile - 1) / tile;
-  const int nb = (nt + threads * R - 1) / (threads * R);
-  const int slots = c->sm_count * pp_occupancy(core, res, fine);
-  const int nchunks = choose_chunks(nb, ntiles, slots, 256);
-  double* partial = nullptr;
-  if (nchunks > 1) {
-    CU(c->partial.reserve((size_t)nchunks * res_ncomp(res) * (size_t)nt * sizeof(double)));
-    partial = c->partial.as<double>();
-  }
-  {
-    PairTimer timer(c);
-    int rc = pp_run_packed(c, core, res, c->packed.as<float4>(), 0, ntiles, INT_MAX, 0, tx, ty, tr, nt, out,
-                           nullptr, nchunks, partial, fine);
-    if (rc) return rc;
-  }
-  if (nchunks > 1) {
-    CU(launch_pp_combine(res, partial, nchunks, nt, out, c->stream));
-    c->launches++;
-  }
-  return O2D_OK;
+  return pp_run_packed(c, core, res, c->packed.as<float4>(), ns_padded, tx, ty, tr, nt, out);
 }
 
 // ---- host staging helpers ----------------------------------------------------------------------------------
@@ -855,7 +862,7 @@ extern "C" int o2d_comm_destroy(o2d_context* c) {
   if (!c) return O2D_OK;
   if (c->comm) {
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->comm_stream);
+    cudaStreamSynchronize(c->stream);
     g_nccl.CommDestroy(c->comm);
     c->comm = nullptr;
   }
@@ -864,57 +871,33 @@ extern "C" int o2d_comm_destroy(o2d_context* c) {
   return O2D_OK;
 }
 
+// Multi-GPU: every rank packs its block of the particles into its slot of one gather buffer (blocks of ns_block
+// entries, rounded up to a pair; shorter blocks are padded with zero-strength entries), ONE in-place ncclAllGather
+// replicates the blocks (16 B per particle over NVLink), and the gathered array is then summed by the same single
+// launch as on one GPU.  The gather sits on the launching stream in front of the sums: it moves 16 B per particle
+// against >= 10^5 pair sums per particle, and a launch that owns the whole device with equal runs is worth more
+// than the fraction of a millisecond an overlapped gather would hide.
 int o2d_pp_sharded_device(o2d_context* c, int core, int res, int ns_local, int ns_block,
                              const float* sx, const float* sy, const float* ss, const float* sr,
                              int nt, const float* tx, const float* ty, const float* tr, const OutPtrs& out) {
   const int P = c->nranks;
-  const int bt = (ns_block + kTile - 1) / kTile;          // tiles per rank block
-  const size_t block_bytes = (size_t)bt * kTile * 16;
-  CU(c->packed_all.reserve(block_bytes * P));
+  const long long blk = ((long long)ns_block + 1) / 2 * 2;                 // entries per rank block
+  const long long ns_padded = (blk * P + kTile - 1) / kTile * kTile;       // gathered array, whole tiles
+  if (ns_padded > INT_MAX) return fail(O2D_ERR_INVALID, "more than 2^31 particles in one evaluation");
+  CU(c->packed_all.reserve((size_t)ns_padded * 16));
   float4* all = c->packed_all.as<float4>();
-  float4* mine = all + (size_t)c->rank * bt * kTile;
-  // pack this rank's block in place inside the gather buffer (padding = zero-strength copies)
-  // (an empty block packs as zero-strength unit-radius particles at the origin)
-  CU(launch_pack_sources(core, ns_local, sx, sy, ss, sr, mine, bt * kTile, c->stream));
+  float4* mine = all + (size_t)c->rank * blk;                              // 2 float4 per pair = 1 per entry
+  CU(launch_pack_sources(core, ns_local, sx, sy, ss, sr, mine, (int)blk, c->stream));
   c->launches++;
-  CU(cudaEventRecord(c->ev_pack, c->stream));
-  // all-gather on the comm stream while the local block is being summed
+  if (ns_padded > blk * P) {   // tail of the last tile: padding only
+    CU(launch_pack_sources(core, ns_local, sx, sy, ss, sr, all + (size_t)blk * P, (int)(ns_padded - blk * P), c->stream, ns_local));
+    c->launches++;
+  }
   if (P > 1) {
-    CU(cudaStreamWaitEvent(c->comm_stream, c->ev_pack, 0));
-    int r = g_nccl.AllGather(mine, all, block_bytes, kNcclChar, c->comm, c->comm_stream);
+    int r = g_nccl.AllGather(mine, all, (size_t)blk * 16, kNcclChar, c->comm, c->stream);
     if (r != 0) return fail(O2D_ERR_COMM, "ncclAllGather: %s", g_nccl.GetErrorString(r));
-    CU(cudaEventRecord(c->ev_gather, c->comm_stream));
   }
-  if (nt <= 0) {
-    if (P > 1) CU(cudaStreamWaitEvent(c->stream, c->ev_gather, 0));
-    return O2D_OK;
-  }
-  const int R = res_targets_per_thread(res);
-  const int nb = (nt + kThreads * R - 1) / (kThreads * R);
-  const int slots = c->sm_count * pp_occupancy(core, res);
-  // chunk the local block and the remote range separately; partial sums from both are combined
-  const int nc_local = choose_chunks(nb, bt, slots, 256);
-  const int rt = bt * (P - 1);
-  const int nc_remote = rt > 0 ? choose_chunks(nb, rt, slots, 256) : 0;
-  const int nchunks = nc_local + nc_remote;
-  CU(c->partial.reserve((size_t)nchunks * res_ncomp(res) * (size_t)nt * sizeof(double)));
-  double* partial = c->partial.as<double>();
-  int cursor = 0;
-  {
-    PairTimer timer(c);
-    int rc = pp_run_packed(c, core, res, all, c->rank * bt, (c->rank + 1) * bt, INT_MAX, 0, tx, ty, tr, nt, out,
-                           &cursor, nc_local, partial);
-    if (rc) return rc;
-    if (rt > 0) {
-      CU(cudaStreamWaitEvent(c->stream, c->ev_gather, 0));
-      // logical tiles [0, rt) hop over this rank's own block
-      rc = pp_run_packed(c, core, res, all, 0, rt, c->rank * bt, bt, tx, ty, tr, nt, out, &cursor, nc_remote, partial);
-      if (rc) return rc;
-    }
-  }
-  CU(launch_pp_combine(res, partial, nchunks, nt, out, c->stream));
-  c->launches++;
-  return O2D_OK;
+  return pp_run_packed(c, core, res, all, ns_padded, tx, ty, tr, nt, out);
 }
 
 extern "C" int o2d_points_on_points_sharded(o2d_context* c, int core, int results, int mem,

@@ -44,9 +44,7 @@ struct o2d_context {
   int sm_count = 0;
   int sm_clock_khz = 0;
   cudaStream_t own_stream = nullptr;
-  cudaStream_t comm_stream = nullptr;
   cudaStream_t stream = nullptr;   // stream in use (own or caller's)
-  cudaEvent_t ev_gather = nullptr, ev_pack = nullptr;
   // scratch
   DevBuf packed, packed_all, partial, panel_packed;
   DevBuf hsrc, htgt, hout, hidx, hpan;   // device mirrors for O2D_MEM_HOST calls

@@ -10,7 +10,9 @@ enum : int { CORE_RM = 0, CORE_EXP = 1, CORE_WL = 2, CORE_V2 = 3, CORE_V3 = 4 };
 // what a pair-sum kernel accumulates (component lists in o2d_pp_impl.cuh)
 enum : int { RES_U = 0, RES_UW = 1, RES_UE = 2, RES_UG = 3, RES_VORT = 4 };
 
-constexpr int kTile = 1024;     // sources per shared-memory tile (16 KiB per stage)
+constexpr int kTile = 1024;     // the packed source array is padded to a multiple of this (also the points-on-panels tile)
+constexpr int kBigTile = 512;   // sources per shared-memory stage of the pair-sum kernels (8 KiB)
+constexpr int kStages = 4;      // stages in flight per CTA (2 ... 16 measured the same)
 constexpr int kThreads = 256;   // threads per CTA of the pair-sum kernels
 constexpr int kMaxOut = 6;
 // "fine" configuration of the same kernel for small problems: a CTA-tile is 128*R x 256 pairs instead of
@@ -23,20 +25,24 @@ struct OutPtrs {
 };
 
 // arguments of one pair-sum launch (passed by value in kernel parameter space)
+//
+// Work of a launch = the (target block, source tile) steps in block-major order, nblocks * ntiles of them.
+// CTA k owns the contiguous run of steps [k*steps_per_cta, (k+1)*steps_per_cta): it walks the tiles of a target
+// block, and when the run crosses into the next block it stores what it has and reloads its targets.  A block
+// that lies inside one run is added straight into the outputs; a block cut between runs leaves its pieces in
+// `partial` (at most two per CTA: the head and the tail of its run) and pp_combine_kernel sums them in CTA order,
+// so the result does not depend on scheduling.
 struct PPArgs {
-  const float4* packed;   // packed source pairs: 2 float4 per pair, kTile float4 per tile
-  int tile_begin;         // logical tile range [tile_begin, tile_end) of this launch
-  int tile_end;
-  int tiles_per_chunk;    // blockIdx.y selects the chunk inside the range
-  int skip_begin;         // logical tiles >= skip_begin map to physical tile + skip_len
-  int skip_len;           //   (multi-GPU: hop over the rank's own block in the gathered array)
-  int chunk_offset;       // first chunk index of this launch inside the partials buffer
+  const float4* packed;      // packed source pairs: 2 float4 per pair, TILE float4 per tile
+  int ntiles;                // tiles of the packed source array
+  int nblocks;               // target blocks of THREADS*R targets
+  long long steps_per_cta;   // S: steps per CTA (the last CTA may own fewer)
   const float* tx;
   const float* ty;
-  const float* tr;        // nullptr: inert targets
+  const float* tr;           // nullptr: inert targets
   int nt;
   OutPtrs out;
-  double* partial;        // nullptr: single chunk, fold straight into `out`
+  double* partial;           // [cta][2][component][THREADS*R]
 };
 
 struct PanelArgs {
@@ -57,25 +63,60 @@ inline int res_ncomp(int res) {
   switch (res) { case 0: return 2; case 1: return 4; case 2: return 3; case 3: return 6; case 4: return 1; }
   return 0;
 }
-inline int res_targets_per_thread(int res, bool fine = false) {
-  const int r = (res == 0 || res == 4) ? 4 : (res == 2 ? 2 : 3);   // mirrors ResTraits<RES>::R
-  return fine ? r / 2 : r;
+// ---- pair-sum kernel shape per (core, result kind, configuration) --------------------------------------------
+// targets per thread R, resident warps per SM the register allocation must allow, and inner-loop unroll (source
+// pairs).  Measured on B200, 1M x 1M (pairs/clk/SM; profiles/r02_pp_shape_search.md): RM and V2 velocity are
+// fastest with 16 resident warps of 128 registers and R = 6 (RM 12.89, V2 12.90; 24 warps of 80 registers with
+// R = 4 give 12.56 / 12.56); WL wants R = 4 (10.75 against 10.37), EXP and V3 24 warps and R = 4 (EXP 11.04
+// against 10.33; V3 with uniform radii 7.53 against 6.91); the gradient-type kernels (128 registers, R = 3) lose
+// to any unrolling (RM velocity+gradient 7.23 / 7.22 / 6.98 / 6.84 at 1 / 2 / 8 / 16).
+constexpr int pp_targets(int core, int res, bool fine) {
+  if (fine) return (res == RES_U || res == RES_VORT) ? 2 : 1;
+  switch (res) {
+    case RES_U:    return (core == CORE_WL || core == CORE_EXP || core == CORE_V3) ? 4 : 6;
+    case RES_VORT: return 4;
+    case RES_UE:   return 2;
+    default:       return 3;   // RES_UW, RES_UG
+  }
+}
+constexpr int pp_min_warps(int core, int res, bool fine) {
+  if (res == RES_VORT || res == RES_UE) return 24;
+  if (res != RES_U) return 16;
+  return (fine || core == CORE_EXP || core == CORE_V3) ? 24 : 16;
+}
+constexpr int pp_unroll(int core, int res, bool fine) {
+  if (fine || core == CORE_EXP || core == CORE_WL) return 4;
+  if (res == RES_UE || res == RES_VORT) return 8;
+  if (res == RES_U) return core == CORE_V3 ? 8 : 16;
+  return 1;
+}
+// threads per CTA.  Coarse configuration: the 16-warp kernels run as ONE 512-thread CTA per SM with one equal run
+// each; the 24-warp kernels as three 256-thread CTAs with short runs (measured as one 768-thread CTA: EXP 10.5
+// against 11.0 pairs/clk/SM, V3 7.2 against 7.3).  See pp_plan (o2d_api.cu).
+constexpr int pp_threads(int core, int res, bool fine) {
+  return fine ? kFineThreads : (pp_min_warps(core, res, false) == 16 ? 512 : kThreads);
+}
+inline int res_targets_per_thread(int core, int res, bool fine = false) { return pp_targets(res == RES_VORT ? CORE_RM : core, res, fine); }
+// targets per block of the (core, res) kernel
+inline int pp_block_targets(int core, int res, bool fine) {
+  const int c = res == RES_VORT ? CORE_RM : core;
+  return pp_threads(c, res, fine) * pp_targets(c, res, fine);
 }
 
 // ---- launchers implemented per translation unit ------------------------------------------------
-// pair-sum kernel for (core, res); grid = (target blocks, nchunks)
-// fine: tile indices in `a` count kFineTile-source tiles and a CTA holds kFineThreads threads
-cudaError_t launch_pp(int core, int res, const PPArgs& a, int nchunks, cudaStream_t st, bool fine = false);
-cudaError_t launch_pp_combine(int res, const double* partial, int nchunks, int nt, const OutPtrs& out,
-                              cudaStream_t st);
+// pair-sum kernel for (core, res); grid = nctas CTAs, each a run of a.steps_per_cta steps
+// fine: tiles in `a` are kFineTile sources and a CTA holds kFineThreads threads
+cudaError_t launch_pp(int core, int res, const PPArgs& a, int nctas, cudaStream_t st, bool fine = false);
+// sums the pieces of the blocks that were cut between CTAs and folds them into a.out (a = the launch it follows)
+cudaError_t launch_pp_combine(int core, int res, const PPArgs& a, cudaStream_t st, bool fine = false);
 // resident CTAs per SM of the (core,res) kernel; cached
 int pp_occupancy(int core, int res, bool fine = false);
 
-// source packing: SoA (x,y,s,r) -> pairwise {-x0,-x1,-y0,-y1}{s0,s1,rho0,rho1}, padded to a whole
-// number of tiles with zero-strength copies of the last particle.  mode: core id, or 100 for
-// the Gaussian-vorticity terms, or 101 for "strength only" (points-on-panels sources).
+// source packing: SoA (x,y,s,r) -> pairwise {-x0,-x1,-y0,-y1}{s0,s1,rho0,rho1}; writes ns_padded (even) entries
+// for sources j0, j0+1, ...: real ones below ns, zero-strength copies of the last particle from ns on.  mode: core
+// id, or 100 for the Gaussian-vorticity terms, or 101 for "strength only" (points-on-panels sources).
 cudaError_t launch_pack_sources(int mode, int ns, const float* sx, const float* sy, const float* ss,
-                                const float* sr, float4* packed, int ns_padded, cudaStream_t st);
+                                const float* sr, float4* packed, int ns_padded, cudaStream_t st, int j0 = 0);
 
 // panels
 cudaError_t launch_pack_panels(int np, const float* nx, const float* ny, const uint32_t* idx,

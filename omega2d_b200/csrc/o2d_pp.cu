@@ -3,6 +3,13 @@
 
 #include <atomic>
 
+#ifdef O2D_PP_DEBUG
+namespace o2d { __device__ unsigned long long o2d_dbg_times[3 * 16384]; }
+extern "C" int o2d_debug_cta_times(unsigned long long* out, int n) {
+  return (int)cudaMemcpyFromSymbol(out, o2d::o2d_dbg_times, sizeof(unsigned long long) * 3 * n);
+}
+#endif
+
 namespace o2d {
 
 template <int CORE> cudaError_t launch_pp_core(int, const PPArgs&, int, cudaStream_t, bool);
@@ -18,15 +25,15 @@ extern template int pp_occupancy_core<CORE_WL>(int, bool);
 extern template int pp_occupancy_core<CORE_V2>(int, bool);
 extern template int pp_occupancy_core<CORE_V3>(int, bool);
 
-cudaError_t launch_pp(int core, int res, const PPArgs& a, int nchunks, cudaStream_t st, bool fine) {
+cudaError_t launch_pp(int core, int res, const PPArgs& a, int nctas, cudaStream_t st, bool fine) {
   if (res == RES_VORT)
-    return fine ? launch_one<CORE_RM, RES_VORT, true>(a, nchunks, st) : launch_one<CORE_RM, RES_VORT, false>(a, nchunks, st);
+    return fine ? launch_one<CORE_RM, RES_VORT, true>(a, nctas, st) : launch_one<CORE_RM, RES_VORT, false>(a, nctas, st);
   switch (core) {
-    case CORE_RM:  return launch_pp_core<CORE_RM>(res, a, nchunks, st, fine);
-    case CORE_EXP: return launch_pp_core<CORE_EXP>(res, a, nchunks, st, fine);
-    case CORE_WL:  return launch_pp_core<CORE_WL>(res, a, nchunks, st, fine);
-    case CORE_V2:  return launch_pp_core<CORE_V2>(res, a, nchunks, st, fine);
-    case CORE_V3:  return launch_pp_core<CORE_V3>(res, a, nchunks, st, fine);
+    case CORE_RM:  return launch_pp_core<CORE_RM>(res, a, nctas, st, fine);
+    case CORE_EXP: return launch_pp_core<CORE_EXP>(res, a, nctas, st, fine);
+    case CORE_WL:  return launch_pp_core<CORE_WL>(res, a, nctas, st, fine);
+    case CORE_V2:  return launch_pp_core<CORE_V2>(res, a, nctas, st, fine);
+    case CORE_V3:  return launch_pp_core<CORE_V3>(res, a, nctas, st, fine);
   }
   return cudaErrorInvalidValue;
 }
@@ -51,15 +58,15 @@ int pp_occupancy(int core, int res, bool fine) {
   return slot.load(std::memory_order_relaxed);
 }
 
-cudaError_t launch_pp_combine(int res, const double* partial, int nchunks, int nt, const OutPtrs& out,
-                              cudaStream_t st) {
-  const int nb = (nt + 255) / 256;
+cudaError_t launch_pp_combine(int core, int res, const PPArgs& a, cudaStream_t st, bool fine) {
+  const int nb = (a.nt + 255) / 256;
+  const int BT = pp_block_targets(core, res, fine);
   switch (res) {
-    case RES_U:    pp_combine_kernel<RES_U><<<nb, 256, 0, st>>>(partial, nchunks, nt, out); break;
-    case RES_UW:   pp_combine_kernel<RES_UW><<<nb, 256, 0, st>>>(partial, nchunks, nt, out); break;
-    case RES_UE:   pp_combine_kernel<RES_UE><<<nb, 256, 0, st>>>(partial, nchunks, nt, out); break;
-    case RES_UG:   pp_combine_kernel<RES_UG><<<nb, 256, 0, st>>>(partial, nchunks, nt, out); break;
-    case RES_VORT: pp_combine_kernel<RES_VORT><<<nb, 256, 0, st>>>(partial, nchunks, nt, out); break;
+    case RES_U:    pp_combine_kernel<RES_U><<<nb, 256, 0, st>>>(a, BT); break;
+    case RES_UW:   pp_combine_kernel<RES_UW><<<nb, 256, 0, st>>>(a, BT); break;
+    case RES_UE:   pp_combine_kernel<RES_UE><<<nb, 256, 0, st>>>(a, BT); break;
+    case RES_UG:   pp_combine_kernel<RES_UG><<<nb, 256, 0, st>>>(a, BT); break;
+    case RES_VORT: pp_combine_kernel<RES_VORT><<<nb, 256, 0, st>>>(a, BT); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -86,8 +93,13 @@ __device__ __forceinline__ float pack_str(int mode, float s, float r) {
   return s;
 }
 
+// Padding entries (index >= ns) carry zero strength and the last real particle's position and radius: they add
+// exactly 0 wherever that particle's own term is finite.  A block without particles (a multi-GPU rank that owns
+// none) is filled with zero-strength entries far from any flow (x = y = 1e6: d2 ~ 2e12 stays finite through d2^3
+// for every core and never meets a target) with a small radius (so they do not raise the EXP core's per-tile
+// radius bound).  j0: index of the first packed entry (j0 = ns writes padding only).
 __global__ void __launch_bounds__(256)
-pack_sources_kernel(int mode, int ns, const float* __restrict__ sx, const float* __restrict__ sy,
+pack_sources_kernel(int mode, int ns, int j0, const float* __restrict__ sx, const float* __restrict__ sy,
                     const float* __restrict__ ss, const float* __restrict__ sr,
                     float4* __restrict__ packed, int npairs) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -95,9 +107,9 @@ pack_sources_kernel(int mode, int ns, const float* __restrict__ sx, const float*
   float x[2], y[2], s[2], rho[2];
 #pragma unroll
   for (int l = 0; l < 2; ++l) {
-    const int j = 2 * p + l;
-    if (ns <= 0) {   // empty block (multi-GPU rank without particles): inert unit-radius filler
-      x[l] = 0.0f; y[l] = 0.0f; s[l] = 0.0f; rho[l] = pack_rho(mode, 1.0f);
+    const int j = j0 + 2 * p + l;
+    if (ns <= 0) {
+      x[l] = -1.0e6f; y[l] = -1.0e6f; s[l] = 0.0f; rho[l] = pack_rho(mode, 1.0e-3f);
       continue;
     }
     const int jj = j < ns ? j : ns - 1;
@@ -112,10 +124,10 @@ pack_sources_kernel(int mode, int ns, const float* __restrict__ sx, const float*
 }
 
 cudaError_t launch_pack_sources(int mode, int ns, const float* sx, const float* sy, const float* ss,
-                                const float* sr, float4* packed, int ns_padded, cudaStream_t st) {
+                                const float* sr, float4* packed, int ns_padded, cudaStream_t st, int j0) {
   const int npairs = ns_padded / 2;
   if (npairs <= 0) return cudaSuccess;
-  pack_sources_kernel<<<(npairs + 255) / 256, 256, 0, st>>>(mode, ns, sx, sy, ss, sr, packed, npairs);
+  pack_sources_kernel<<<(npairs + 255) / 256, 256, 0, st>>>(mode, ns, j0, sx, sy, ss, sr, packed, npairs);
   return cudaGetLastError();
 }
 

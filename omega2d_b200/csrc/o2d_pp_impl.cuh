@@ -5,20 +5,21 @@
 // (src/InfluenceVort.h:106-118).
 //
 // Work decomposition
-//   grid.x = target blocks of THREADS*R targets, grid.y = source chunks of `tiles_per_chunk` tiles.
-//   A thread owns R targets in registers for its whole life and walks its chunk of the packed
-//   source array tile by tile.  Source tiles (TILE sources = TILE*16 bytes) are staged into
-//   shared memory by ONE TMA bulk copy per tile (cp.async.bulk + mbarrier), double buffered, and
-//   read back with warp-broadcast LDS.128.
+//   The launch's work is the sequence of (target block, source tile) steps in block-major order; every CTA
+//   owns an equal contiguous run of it (PPArgs, o2d_internal.h), so all CTAs of a launch that fills the
+//   machine once finish together whatever the particle count -- there is no last wave.  A thread owns R targets
+//   in registers while its CTA walks the tiles of their block.  Source tiles (TILE sources = TILE*16 bytes)
+//   are staged into shared memory by ONE TMA bulk copy per tile (cp.async.bulk + mbarrier), double buffered
+//   across block boundaries too, and read back with warp-broadcast LDS.128.
 // Arithmetic
 //   Sources are stored pairwise -- {x0,x1,y0,y1} {s0,s1,rho0,rho1} -- so that one LDS.128 feeds
 //   both lanes of Blackwell's packed FP32 instructions (FADD2/FMUL2/FFMA2): every FP32
 //   instruction in the inner loop evaluates two source-target pairs.
 // Accumulation (SURVEY 7 "hard parts": a single FP32 accumulator fails the 1e-5 tolerance)
 //   per tile: float partial sums (two lanes x TILE/2 terms), folded into float64 once per tile;
-//   the float64 sums are either added straight into the float outputs ("tu[i] += accum", as the
-//   reference) when the launch has one source chunk, or written to a partials buffer that
-//   o2d_pp_combine sums in fixed chunk order -- results are bit-reproducible run to run.
+//   the float64 sums of a block that lies inside one CTA's run are added straight into the float
+//   outputs ("tu[i] += accum", as the reference); the pieces of a block cut between CTAs go to a
+//   partials buffer that pp_combine_kernel sums in fixed CTA order -- results are bit-reproducible.
 #pragma once
 #include "o2d_device.cuh"
 #include "o2d_internal.h"
@@ -33,11 +34,11 @@ namespace o2d {
 //   RES_VORT : W = sum c exp2(-d2 a)      (Gaussian vorticity; a = log2e/sr^2, c = 2 ss/sr^2)
 // how they map onto the reference's per-pair updates is in apply_outputs() below.
 template <int RES> struct ResTraits;
-template <> struct ResTraits<RES_U>    { static constexpr int NCOMP = 2; static constexpr int R = 4; static constexpr bool GRAD = false; };
-template <> struct ResTraits<RES_UW>   { static constexpr int NCOMP = 4; static constexpr int R = 3; static constexpr bool GRAD = true; };
-template <> struct ResTraits<RES_UE>   { static constexpr int NCOMP = 3; static constexpr int R = 2; static constexpr bool GRAD = true; };
-template <> struct ResTraits<RES_UG>   { static constexpr int NCOMP = 6; static constexpr int R = 3; static constexpr bool GRAD = true; };
-template <> struct ResTraits<RES_VORT> { static constexpr int NCOMP = 1; static constexpr int R = 4; static constexpr bool GRAD = false; };
+template <> struct ResTraits<RES_U>    { static constexpr int NCOMP = 2; static constexpr bool GRAD = false; };
+template <> struct ResTraits<RES_UW>   { static constexpr int NCOMP = 4; static constexpr bool GRAD = true; };
+template <> struct ResTraits<RES_UE>   { static constexpr int NCOMP = 3; static constexpr bool GRAD = true; };
+template <> struct ResTraits<RES_UG>   { static constexpr int NCOMP = 6; static constexpr bool GRAD = true; };
+template <> struct ResTraits<RES_VORT> { static constexpr int NCOMP = 1; static constexpr bool GRAD = false; };
 
 // Fold the float64 component sums of one target into the float outputs exactly like the
 // reference's epilogue "tu[0][i] += accumu" (float += double; src/Influence.h:359-360,378-380).
@@ -173,143 +174,190 @@ __device__ __forceinline__ void tile_sum(const float4* __restrict__ s, const flo
   }
 }
 
-template <int CORE, int RES, int THREADS, int TILE, int R = ResTraits<RES>::R, int UNROLL = 4>
-__global__ void __launch_bounds__(THREADS)
+#ifdef O2D_PP_DEBUG
+// development only: per-CTA (smid, start, end) of the last pair-sum launch, read back by o2d_debug_cta_times
+extern __device__ unsigned long long o2d_dbg_times[3 * 16384];
+__device__ __forceinline__ unsigned long long dbg_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned dbg_smid() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+#endif
+
+// Pipeline: the CTA's warps share the staged tiles but never wait for each other.  Stage s is filled by a TMA bulk
+// copy that completes on full[s]; every warp waits for it, sums the tile onto its own targets and then counts
+// itself off on done[s]; the warp that counts off LAST refills the stage with the tile NS steps further along the
+// run.  There is no CTA-wide barrier anywhere in the walk: a warp's targets, its block boundaries and its stores
+// are its own business.  (Measured: the warps of an SM drift apart and stay apart, which is what keeps the FMA and
+// the XU pipe busy at the same time -- warps that run in step all queue for the same pipe at the same moment; a
+// version with one __syncthreads per tile and all CTAs starting together ran 12 % slower.)
+// Resident warps per SM the register allocation must allow: 24 (<= 85 registers) for the velocity and Gaussian-
+// vorticity kernels, 16 (<= 128) for the gradient-type results.  Left to itself ptxas takes 104-126 registers for
+// some velocity instances and halves their occupancy.
+// (shape per core and result kind: pp_targets / pp_min_warps / pp_unroll in o2d_internal.h.  Left to itself ptxas
+// takes 104-126 registers for some instances and others spill at 80; the resident-warp bound pins the allocation.)
+template <int CORE, int RES, int THREADS, int TILE, int R, int UNROLL>
+__global__ void __launch_bounds__(THREADS, pp_min_warps(CORE, RES, THREADS == kFineThreads) * 32 / THREADS)
 pp_kernel(const PPArgs a) {
   using T = ResTraits<RES>;
   constexpr int NC = T::NCOMP;
+  constexpr int NS = kStages;
+  constexpr int NWARPS = THREADS / 32;
   constexpr uint32_t TILE_BYTES = TILE * 16;
+  constexpr int BT = THREADS * R;   // targets per block
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float4* stage0 = reinterpret_cast<float4*>(smem_raw);
-  float4* stage1 = reinterpret_cast<float4*>(smem_raw + TILE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * TILE_BYTES);
-  __shared__ float wmax[2 * (THREADS / 32)];   // EXP core: per-warp maxima of the tile's radius terms, double buffered
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + NS * TILE_BYTES);
+  int* done = reinterpret_cast<int*>(smem_raw + NS * TILE_BYTES + NS * 8);
+  auto stage = [&](int s) { return reinterpret_cast<const float4*>(smem_raw + (size_t)s * TILE_BYTES); };
 
   const int tid = threadIdx.x;
-  const int tile_begin = a.tile_begin + blockIdx.y * a.tiles_per_chunk;
-  const int tile_end = min(tile_begin + a.tiles_per_chunk, a.tile_end);
-  const int ntiles = tile_end - tile_begin;
+  const int lane = tid & 31;
+#ifdef O2D_PP_DEBUG
+  if (tid == 0 && blockIdx.x < 16384) { o2d_dbg_times[3 * blockIdx.x] = dbg_smid(); o2d_dbg_times[3 * blockIdx.x + 1] = dbg_globaltimer(); }
+#endif
+  // this CTA's run of (block, tile) steps
+  const long long total = (long long)a.nblocks * a.ntiles;
+  const long long run_begin = (long long)blockIdx.x * a.steps_per_cta;
+  if (run_begin >= total) return;
+  const int nsteps = (int)(min(run_begin + a.steps_per_cta, total) - run_begin);
+  int block = (int)(run_begin / a.ntiles);
+  int tile = (int)(run_begin - (long long)block * a.ntiles);
 
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); done[s] = 0; }
     mbar_fence_init();
-  }
-  __syncthreads();
-  // logical -> physical tile (TILE float4 per tile: 2 per source pair)
-  auto tile_ptr = [&](int lt) -> const float4* {
-    const int pt = lt >= a.skip_begin ? lt + a.skip_len : lt;
-    return a.packed + (size_t)pt * TILE;
-  };
-  if (tid == 0 && ntiles > 0) {
-    mbar_arrive_expect_tx(&bars[0], TILE_BYTES);
-    tma_load_1d(stage0, tile_ptr(tile_begin), TILE_BYTES, &bars[0]);
-  }
-
-  // ---- this thread's targets ------------------------------------------------------------------
-  const int tbase = blockIdx.x * (THREADS * R) + tid;
-  float2 tx[R], ty[R], tau[R];
 #pragma unroll
-  for (int k = 0; k < R; ++k) {
-    const int i = tbase + k * THREADS;
-    const bool ok = i < a.nt;
-    tx[k] = f2(ok ? a.tx[i] : 0.0f);
-    ty[k] = f2(ok ? a.ty[i] : 0.0f);
-    float t = 0.0f;
-    if (RES != RES_VORT && a.tr != nullptr && ok) t = radius_term<CORE>(a.tr[i]);
-    tau[k] = f2(t);
-  }
-  // every thread's R targets share one radius term (inert targets; uniform-radius particle sets,
-  // the reference's normal case): take the cheaper tile_sum<UNI>.  The flag is made CTA-uniform so
-  // the tile loop's barriers stay convergent.  Out-of-range targets carry 0: they only send the
-  // last CTA of a blob-target launch down the general path.
-  bool uni_t = true;
-#pragma unroll
-  for (int k = 1; k < R; ++k) uni_t = uni_t && (tau[k].x == tau[0].x);
-  const bool uni = __syncthreads_and(uni_t) != 0;
-
-  double acc[R][NC];
-#pragma unroll
-  for (int k = 0; k < R; ++k)
-#pragma unroll
-    for (int c = 0; c < NC; ++c) acc[k][c] = 0.0;
-
-  // ---- walk the source tiles --------------------------------------------------------------------
-  for (int t = 0; t < ntiles; ++t) {
-    // every thread is done with tile t-1, so its stage may be overwritten by the prefetch of t+1
-    __syncthreads();
-    if (tid == 0 && t + 1 < ntiles) {
-      uint64_t* bar = &bars[(t + 1) & 1];
-      mbar_arrive_expect_tx(bar, TILE_BYTES);
-      tma_load_1d((t + 1) & 1 ? stage1 : stage0, tile_ptr(tile_begin + t + 1), TILE_BYTES, bar);
-    }
-    mbar_wait(&bars[t & 1], (uint32_t)((t >> 1) & 1));
-    const float4* s = (t & 1) ? stage1 : stage0;
-
-    // EXP core: largest source radius term of the tile (CTA-wide max of the rho lanes; radius terms are >= 0)
-    float rho_max = 0.0f;
-    if (CORE == CORE_EXP && RES != RES_VORT) {
-      float m = 0.0f;
-      for (int p = tid; p < TILE / 2; p += THREADS) { const float4 B = s[2 * p + 1]; m = fmaxf(m, fmaxf(B.z, B.w)); }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-      if ((tid & 31) == 0) wmax[(t & 1) * (THREADS / 32) + (tid >> 5)] = m;
-      __syncthreads();
-#pragma unroll
-      for (int w = 0; w < THREADS / 32; ++w) rho_max = fmaxf(rho_max, wmax[(t & 1) * (THREADS / 32) + w]);
-    }
-
-    float2 part[R][NC];
-#pragma unroll
-    for (int k = 0; k < R; ++k)
-#pragma unroll
-      for (int c = 0; c < NC; ++c) part[k][c] = f2(0.0f);
-
-    if (uni) tile_sum<CORE, RES, TILE, R, UNROLL, true>(s, tx, ty, tau, part, rho_max);
-    else     tile_sum<CORE, RES, TILE, R, UNROLL, false>(s, tx, ty, tau, part, rho_max);
-    // fold this tile's float partial sums into the float64 accumulators
-#pragma unroll
-    for (int k = 0; k < R; ++k)
-#pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        const double sum = (double)part[k][c].x + (double)part[k][c].y;
-        acc[k][c] += bb_fold_scale<CORE, RES>(c) * sum;
+    for (int s = 0; s < NS; ++s)
+      if (s < nsteps) {
+        mbar_arrive_expect_tx(&full[s], TILE_BYTES);
+        tma_load_1d(smem_raw + (size_t)s * TILE_BYTES, a.packed + (size_t)((tile + s) % a.ntiles) * TILE, TILE_BYTES, &full[s]);
       }
   }
+  __syncthreads();   // the only CTA-wide barrier: the mbarriers exist before anyone polls them
 
-  // ---- epilogue -----------------------------------------------------------------------------------
+  int step = 0;   // steps done by this warp; stage = step % NS, mbarrier phase = (step / NS) & 1
+  for (int seg = 0; step < nsteps; ++seg, ++block, tile = 0) {
+    const int seg_tiles = min(a.ntiles - tile, nsteps - step);
+
+    // ---- this thread's targets ------------------------------------------------------------------
+    const int tbase = block * BT + tid;
+    float2 tx[R], ty[R], tau[R];
 #pragma unroll
-  for (int k = 0; k < R; ++k) {
-    const int i = tbase + k * THREADS;
-    if (i >= a.nt) continue;
-    if (a.partial == nullptr) {
-      apply_outputs<RES>(a.out, i, acc[k]);
+    for (int k = 0; k < R; ++k) {
+      const int i = tbase + k * THREADS;
+      const bool ok = i < a.nt;
+      tx[k] = f2(ok ? a.tx[i] : 0.0f);
+      ty[k] = f2(ok ? a.ty[i] : 0.0f);
+      float t = 0.0f;
+      if (RES != RES_VORT && a.tr != nullptr && ok) t = radius_term<CORE>(a.tr[i]);
+      tau[k] = f2(t);
+    }
+    // every lane's R targets share one radius term (inert targets; uniform-radius particle sets, the
+    // reference's normal case): the warp takes the cheaper tile_sum<UNI>.  Out-of-range targets carry 0:
+    // they only send the last warps of a blob-target launch down the general path.
+    bool uni_t = true;
+#pragma unroll
+    for (int k = 1; k < R; ++k) uni_t = uni_t && (tau[k].x == tau[0].x);
+    const bool uni = __all_sync(0xffffffffu, uni_t);
+
+    double acc[R][NC];
+#pragma unroll
+    for (int k = 0; k < R; ++k)
+#pragma unroll
+      for (int c = 0; c < NC; ++c) acc[k][c] = 0.0;
+
+    // ---- walk the segment's source tiles ----------------------------------------------------------
+    for (int j = 0; j < seg_tiles; ++j, ++step) {
+      const int st = step % NS;
+      mbar_wait(&full[st], (uint32_t)((step / NS) & 1));
+      const float4* s = stage(st);
+
+      // EXP core: largest source radius term of the tile (radius terms are >= 0)
+      float rho_max = 0.0f;
+      if (CORE == CORE_EXP && RES != RES_VORT) {
+        for (int p = lane; p < TILE / 2; p += 32) { const float4 B = s[2 * p + 1]; rho_max = fmaxf(rho_max, fmaxf(B.z, B.w)); }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) rho_max = fmaxf(rho_max, __shfl_xor_sync(0xffffffffu, rho_max, off));
+      }
+
+      float2 part[R][NC];
+#pragma unroll
+      for (int k = 0; k < R; ++k)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) part[k][c] = f2(0.0f);
+
+      if (uni) tile_sum<CORE, RES, TILE, R, UNROLL, true>(s, tx, ty, tau, part, rho_max);
+      else     tile_sum<CORE, RES, TILE, R, UNROLL, false>(s, tx, ty, tau, part, rho_max);
+
+      // this warp is done with the stage; the last warp to say so refills it
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence_block();
+        if (atomicAdd(&done[st], 1) == NWARPS - 1) {
+          done[st] = 0;
+          if (step + NS < nsteps) {
+            mbar_arrive_expect_tx(&full[st], TILE_BYTES);
+            tma_load_1d(smem_raw + (size_t)st * TILE_BYTES, a.packed + (size_t)((tile + j + NS) % a.ntiles) * TILE,
+                        TILE_BYTES, &full[st]);
+          }
+        }
+      }
+      // fold this tile's float partial sums into the float64 accumulators
+#pragma unroll
+      for (int k = 0; k < R; ++k)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const double sum = (double)part[k][c].x + (double)part[k][c].y;
+          acc[k][c] += bb_fold_scale<CORE, RES>(c) * sum;
+        }
+    }
+
+    // ---- end of the segment -------------------------------------------------------------------------
+#ifdef O2D_PP_DEBUG
+    if (tid == THREADS - 1 && blockIdx.x < 16384) o2d_dbg_times[3 * blockIdx.x + 2] = dbg_globaltimer();
+#endif
+    if (seg_tiles == a.ntiles) {
+      // the whole block was summed here: "tu[i] += accum" as the reference does
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        const int i = tbase + k * THREADS;
+        if (i < a.nt) apply_outputs<RES>(a.out, i, acc[k]);
+      }
     } else {
-      // partial[(chunk*NC + c) * nt + i], coalesced over i
-      double* dst = a.partial + ((size_t)(a.chunk_offset + blockIdx.y) * NC) * (size_t)a.nt + i;
+      // a run begins and ends with a piece of a block at most: slot 0 = the piece in the run's first block, slot 1 = the
+      // other.  partial[((cta * 2 + slot) * NC + c) * BT + k*THREADS + tid], coalesced over tid
+      double* dst = a.partial + ((size_t)blockIdx.x * 2 + (seg == 0 ? 0 : 1)) * (size_t)(NC * BT) + tid;
 #pragma unroll
-      for (int c = 0; c < NC; ++c) dst[(size_t)c * a.nt] = acc[k][c];
+      for (int k = 0; k < R; ++k)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) dst[c * BT + k * THREADS] = acc[k][c];
     }
   }
 }
 
-// sum the per-chunk float64 partials in fixed chunk order, then fold into the outputs
+// Blocks that were cut between CTAs: sum the pieces in CTA order (fixed by the launch geometry, not by scheduling),
+// then fold into the outputs.  Block b = steps [b*ntiles, (b+1)*ntiles) lies in the runs of CTAs
+// k0 = b*ntiles/S .. k1 = ((b+1)*ntiles-1)/S; k0 == k1 means one CTA had all of it and has already added it.
 template <int RES>
 __global__ void __launch_bounds__(256)
-pp_combine_kernel(const double* __restrict__ partial, int nchunks, int nt, const OutPtrs out) {
+pp_combine_kernel(const PPArgs a, int BT) {
   constexpr int NC = ResTraits<RES>::NCOMP;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nt) return;
+  if (i >= a.nt) return;
+  const int b = i / BT, li = i - b * BT;
+  const long long S = a.steps_per_cta;
+  const long long first = (long long)b * a.ntiles;
+  const int k0 = (int)(first / S), k1 = (int)((first + a.ntiles - 1) / S);
+  if (k0 == k1) return;
   double c[NC];
 #pragma unroll
   for (int k = 0; k < NC; ++k) c[k] = 0.0;
-  for (int ch = 0; ch < nchunks; ++ch) {
-    const double* src = partial + ((size_t)ch * NC) * (size_t)nt + i;
+  for (int k = k0; k <= k1; ++k) {
+    const int slot = (int)(((long long)k * S) / a.ntiles) == b ? 0 : 1;
+    const double* src = a.partial + ((size_t)k * 2 + slot) * (size_t)(NC * BT) + li;
 #pragma unroll
-    for (int k = 0; k < NC; ++k) c[k] += src[(size_t)k * nt];
+    for (int q = 0; q < NC; ++q) c[q] += src[q * BT];
   }
-  apply_outputs<RES>(out, i, c);
+  apply_outputs<RES>(a.out, i, c);
 }
 
 }  // namespace o2d
@@ -319,25 +367,22 @@ namespace o2d {
 
 template <int CORE, int RES, bool FINE>
 struct PPConfig {
-  static constexpr int THREADS = FINE ? kFineThreads : kThreads;
-  static constexpr int TILE = FINE ? kFineTile : kTile;
-  static constexpr int R = FINE ? ResTraits<RES>::R / 2 : ResTraits<RES>::R;
-  static constexpr size_t SMEM = 2 * (size_t)TILE * 16 + 64;
-  // inner-loop unroll: 8 source pairs for the big configuration (4 for the branchy EXP core), 4 for the small tiles
-  static constexpr int UNROLL = (FINE || CORE == CORE_EXP) ? 4 : 8;
+  static constexpr int THREADS = pp_threads(CORE, RES, FINE);
+  static constexpr int TILE = FINE ? kFineTile : kBigTile;
+  static constexpr int R = pp_targets(CORE, RES, FINE);
+  static constexpr size_t SMEM = kStages * ((size_t)TILE * 16 + 8 + 4);
+  static constexpr int UNROLL = pp_unroll(CORE, RES, FINE);
   static auto kernel() { return pp_kernel<CORE, RES, THREADS, TILE, R, UNROLL>; }
 };
 
 template <int CORE, int RES, bool FINE>
-static cudaError_t launch_one(const PPArgs& a, int nchunks, cudaStream_t st) {
+static cudaError_t launch_one(const PPArgs& a, int nctas, cudaStream_t st) {
   using C = PPConfig<CORE, RES, FINE>;
   auto kern = C::kernel();
-  // two 16 KiB stages + barriers: under the 48 KiB a kernel gets without opting in, so there is no per-device
+  // four 8 KiB stages + barriers: under the 48 KiB a kernel gets without opting in, so there is no per-device
   // function attribute to set (a process may drive several devices, o2d_group.cu)
   static_assert(C::SMEM <= 48 * 1024, "dynamic shared memory above the default limit needs cudaFuncSetAttribute per device");
-  const int nb = (a.nt + C::THREADS * C::R - 1) / (C::THREADS * C::R);
-  dim3 grid(nb, nchunks, 1);
-  kern<<<grid, C::THREADS, C::SMEM, st>>>(a);
+  kern<<<nctas, C::THREADS, C::SMEM, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -351,19 +396,19 @@ static int occupancy_one() {
 }
 
 template <int CORE, bool FINE>
-static cudaError_t launch_pp_core_cfg(int res, const PPArgs& a, int nchunks, cudaStream_t st) {
+static cudaError_t launch_pp_core_cfg(int res, const PPArgs& a, int nctas, cudaStream_t st) {
   switch (res) {
-    case RES_U:  return launch_one<CORE, RES_U, FINE>(a, nchunks, st);
-    case RES_UW: return launch_one<CORE, RES_UW, FINE>(a, nchunks, st);
-    case RES_UE: return launch_one<CORE, RES_UE, FINE>(a, nchunks, st);
-    case RES_UG: return launch_one<CORE, RES_UG, FINE>(a, nchunks, st);
+    case RES_U:  return launch_one<CORE, RES_U, FINE>(a, nctas, st);
+    case RES_UW: return launch_one<CORE, RES_UW, FINE>(a, nctas, st);
+    case RES_UE: return launch_one<CORE, RES_UE, FINE>(a, nctas, st);
+    case RES_UG: return launch_one<CORE, RES_UG, FINE>(a, nctas, st);
   }
   return cudaErrorInvalidValue;
 }
 
 template <int CORE>
-cudaError_t launch_pp_core(int res, const PPArgs& a, int nchunks, cudaStream_t st, bool fine) {
-  return fine ? launch_pp_core_cfg<CORE, true>(res, a, nchunks, st) : launch_pp_core_cfg<CORE, false>(res, a, nchunks, st);
+cudaError_t launch_pp_core(int res, const PPArgs& a, int nctas, cudaStream_t st, bool fine) {
+  return fine ? launch_pp_core_cfg<CORE, true>(res, a, nctas, st) : launch_pp_core_cfg<CORE, false>(res, a, nctas, st);
 }
 
 template <int CORE, bool FINE>
