@@ -143,7 +143,7 @@ def _panel_check(got, want, exact):
 @pytest.mark.parametrize("npan,nt", [(1, 5), (143, 10000), (257, 300), (5000, 4096)])
 def test_panels_vs_oracle(npan, nt, ctx, port):
     """Smooth sheet strengths (flow-over-cylinder like: vs ~ sin(theta)), the physically relevant case."""
-    from f64ref import panels_on_points_f64, points_on_panels_f64
+    from oracle.f64 import panels_on_points_f64, points_on_panels_f64
     nx, ny, idx, vs, ss = W.circle_panels(max(npan, 3), radius=0.5, seed=npan)
     th = np.arctan2(ny, nx)
     vs = (2.0 * np.sin(th) + 0.3).astype(np.float32); ss = (0.5 * np.cos(th)).astype(np.float32)
@@ -161,7 +161,7 @@ def test_panels_vs_oracle(npan, nt, ctx, port):
 def test_panels_random_strengths_noise_floor(ctx, port):
     """5000 short panels with RANDOM +-1 strengths: the far field nearly cancels and the float32
     reference formulation carries rounding noise above 1e-5 of max|u| by itself (3.8e-5 here)."""
-    from f64ref import panels_on_points_f64
+    from oracle.f64 import panels_on_points_f64
     nx, ny, idx, vs, ss = W.circle_panels(5000, radius=0.5, seed=5000)
     x, y, _, _ = W.annulus_blobs(2048, seed=4096)
     want = port.panels_on_points(nx, ny, idx, vs, ss, x, y)
@@ -393,7 +393,7 @@ def _ring_targets(cx, cy, length, nrho=240, nphi=48, lo=-1.5, hi=2.5):
 def test_panel_near_far_transition_pointwise(length, angle, ctx):
     """ONE panel, vortex + source strength: every target separately within 3e-6 of exact (float64) arithmetic,
     relative to the local velocity magnitude (the reference's own float32 form is up to 1e-4 off here)."""
-    from f64ref import panels_on_points_f64
+    from oracle.f64 import panels_on_points_f64
     nx = np.array([0.3, 0.3 + length * np.cos(angle)], np.float32)
     ny = np.array([0.2, 0.2 + length * np.sin(angle)], np.float32)
     idx = np.array([0, 1], np.uint32)
@@ -408,7 +408,7 @@ def test_panel_near_far_transition_pointwise(length, angle, ctx):
 def test_points_on_panels_near_far_transition_pointwise(ctx):
     """ONE particle against many panels of different length, orientation and distance: each panel's velocity is a
     single pair, so the check is pointwise.  Exact = float64."""
-    from f64ref import points_on_panels_f64
+    from oracle.f64 import points_on_panels_f64
     rng = np.random.default_rng(11)
     npan = 6000
     length = 10 ** rng.uniform(-3, -1, npan)

@@ -138,7 +138,7 @@ npan = vs.size
 th = 2.0 * np.pi * (np.arange(npan) % (args.panels // 4)) / (args.panels // 4)
 vs = (2.0 * np.sin(th) + 0.3).astype(np.float32); ss = (0.5 * np.cos(th)).astype(np.float32)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from f64ref import panels_on_points_f64, points_on_panels_f64
+from oracle.f64 import panels_on_points_f64, points_on_panels_f64
 area = np.hypot(nx[idx[1::2]] - nx[idx[0::2]], ny[idx[1::2]] - ny[idx[0::2]]).astype(np.float32)
 dp = [T(a) for a in (nx, ny, vs, ss, area)]
 didx = T(idx.astype(np.int32))
