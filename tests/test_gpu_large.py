@@ -56,3 +56,87 @@ def test_linearity_in_strength(ctx):
     b = _device_eval(ctx, "v2", o2d.VELONLY, arrs2, 2)
     np.testing.assert_array_equal(b[0], 2 * a[0])
     np.testing.assert_array_equal(b[1], 2 * a[1])
+
+
+# ---- BASELINE configs[3] (C4) and C5-like sizes against reference-generated fixtures ---------------------------------
+@pytest.fixture(scope="module")
+def large():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_golden_large.npz"))
+
+
+def _check_inputs(arrs, checksum):
+    got = np.array([a.astype(np.float64).sum() for a in arrs])
+    np.testing.assert_allclose(got, checksum, rtol=1e-12, err_msg="seeded generator no longer reproduces the fixture's inputs")
+
+
+def _panel_rule(got, ref, exact, what):
+    """README "Parity rule for panels": within 1e-5 of the reference, or -- where the reference's float32 form is
+    itself further than that from float64 -- within 1e-5 of float64 and no further from the reference than 1.5x the
+    reference's own error."""
+    e_ref, e_f64, noise = W.rel_err(got, ref), W.rel_err(got, exact), W.rel_err(ref, exact)
+    assert e_ref <= TOL or (e_f64 <= TOL and e_ref <= 1.5 * noise), (what, "vs reference", e_ref, "vs float64", e_f64, "reference vs float64", noise)
+    return e_ref, e_f64, noise
+
+
+def test_c4_find_vels_4m_particles_20k_panels(ctx, large):
+    """C4 shape on one GPU: the whole find_vels (zero, 4M x 4M particle sums, 20k panels on 4M particles, finalize) with
+    device arrays; 512 strided targets against the reference's own find_vels."""
+    import torch
+    n = 4_194_304
+    arrs = W.gaussian_blob(n, seed=2024)
+    _check_inputs(arrs, large["c4_input_checksum"])
+    sub = large["c4_sub"]
+    np.testing.assert_array_equal(arrs[0][sub], large["c4_tx"])
+    nx, ny, idx, vs, ss = W.multi_circle_panels(4, 5000)
+    np.testing.assert_array_equal(vs, large["c4_random_vs"])
+    dev = torch.device("cuda:0")
+    d = [torch.from_numpy(a).to(dev) for a in arrs]
+    pd = [torch.from_numpy(a).to(dev) for a in (nx, ny, idx.astype(np.int32), vs, ss)]
+    tu = torch.empty(n, device=dev); tv = torch.empty(n, device=dev)
+    ctx.find_vels("rm", o2d.VELONLY, o2d.MEM_DEVICE, n, d[0], d[1], d[2], d[3], vs.size, nx.size, *pd,
+                  n, d[0], d[1], d[3], tu, tv, None, (0.0, 0.0))
+    ctx.synchronize()
+    isub = torch.from_numpy(sub).to(dev)
+    got = (tu[isub].cpu().numpy(), tv[isub].cpu().numpy())
+    k = 0.5 / np.pi
+    for tag, g in (("random", got),):
+        ref = tuple(large[f"c4_{tag}_find_vels"])
+        pr, pe = large[f"c4_{tag}_panels_ref"], large[f"c4_{tag}_panels_f64"]
+        # the reference's total with its float32 panel term replaced by the float64 evaluation of the same formula
+        exact = (ref[0].astype(np.float64) + k * (pe[0] - pr[0]), ref[1].astype(np.float64) + k * (pe[1] - pr[1]))
+        _panel_rule(g, ref, exact, f"find_vels total, {tag} strengths")
+    # the N^2 part alone is within the plain tolerance of the reference (un-normalised sums)
+    pu = torch.zeros(512, device=dev); pv = torch.zeros(512, device=dev)
+    t = [torch.from_numpy(large[k_]).to(dev) for k_ in ("c4_tx", "c4_ty", "c4_tr")]
+    ctx.points_on_points("rm", o2d.VELONLY, o2d.MEM_DEVICE, n, d[0], d[1], d[2], d[3], 512, t[0], t[1], t[2], pu, pv)
+    ctx.synchronize()
+    assert W.rel_err((pu.cpu().numpy(), pv.cpu().numpy()), tuple(large["c4_particles_ref"])) < TOL
+    # smooth (BEM-like) sheet strengths: whole find_vels on the sampled targets, and the panel term by itself
+    svs, sss = large["c4_smooth_vs"], large["c4_smooth_ss"]
+    g = ctx.find_vels_np("rm", o2d.VELONLY, arrs, (nx, ny, idx, svs, sss), large["c4_tx"], large["c4_ty"], large["c4_tr"])
+    ref = tuple(large["c4_smooth_find_vels"])
+    pr, pe = large["c4_smooth_panels_ref"], large["c4_smooth_panels_f64"]
+    exact = (ref[0].astype(np.float64) + k * (pe[0] - pr[0]), ref[1].astype(np.float64) + k * (pe[1] - pr[1]))
+    _panel_rule(g[:2], ref, exact, "find_vels total, smooth strengths")
+    for tag, pvs, pss in (("random", vs, ss), ("smooth", svs, sss)):
+        gp = ctx.panels_on_points_np(nx, ny, idx, pvs, pss, large["c4_tx"], large["c4_ty"])
+        e_ref, e_f64, noise = _panel_rule(gp, tuple(large[f"c4_{tag}_panels_ref"]), tuple(large[f"c4_{tag}_panels_f64"]), f"panel term, {tag}")
+        assert e_f64 < TOL     # against exact arithmetic the CUDA panel term is always inside the tolerance
+
+
+@pytest.mark.parametrize("core", ["wl", "v2"])
+def test_2m_particles_wl_and_v2(core, ctx, large):
+    """2 097 152 x 2 097 152 pair sums with the C5 core (Winckelmans-Leonard) and the reference's default core (Vatistas-2):
+    the accumulation error grows with N, so the large sizes are pinned separately (256 strided targets, reference-generated)."""
+    n = 2_097_152
+    arrs = W.gaussian_blob(n, seed=2024)
+    _check_inputs(arrs, large["m2_input_checksum"])
+    u, v = _device_eval(ctx, core, o2d.VELONLY, arrs, 2)
+    sub = large["m2_sub"]
+    ref = large[f"m2_{core}"]
+    scale = np.sqrt(u.astype(np.float64) ** 2 + v.astype(np.float64) ** 2).max()
+    err = np.sqrt((u[sub] - ref[0]).astype(np.float64) ** 2 + (v[sub] - ref[1]).astype(np.float64) ** 2).max() / scale
+    assert err < TOL, err
+    gsum = abs(np.dot(arrs[2].astype(np.float64), u.astype(np.float64))) / (np.abs(arrs[2]).sum() * scale)
+    assert gsum < 1e-5
