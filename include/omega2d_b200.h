@@ -167,11 +167,11 @@ int o2d_find_vels(o2d_context* ctx, int core, int results, int mem,
  * (order 2, :314-392) or advect_3rd (order 3, :472-595) with ElementBase::move
  * (src/ElementBase.h:276-359) between the find_vels evaluations.  x,y are advanced in place;
  * u,v receive what the reference leaves in the collection's velocity arrays (the weighted
- * stage velocities for order 2 and 3).  Surface strengths pvs/pss are held fixed over the
- * step: the reference re-solves its BEM (Eigen, host) and runs clear_inner_layer between
- * stages, which are outside this library, so for flows with bodies the caller keeps driving
- * the stages itself through o2d_find_vels; for particle-only flows (np == 0, e.g. the
- * reference's examples/speedtest20kx10.json) this is the reference's whole convection step.
+ * stage velocities for order 2 and 3).  For particle-only flows (np == 0, e.g. the reference's
+ * examples/speedtest20kx10.json) this is the reference's whole convection step.  With np > 0 the
+ * surface strengths pvs/pss are held FIXED over the step and clear_inner_layer is NOT run -- a
+ * frozen-body approximation kept for callers that handle both themselves; the reference's own
+ * step with bodies (BEM re-solved and inner layer cleared after every stage) is o2d_advect_bodies.
  */
 int o2d_advect(o2d_context* ctx, int core, int order, int mem,
                int n, float* x, float* y, const float* s, const float* r, float* u, float* v,
@@ -188,6 +188,35 @@ int o2d_advect_steps(o2d_context* ctx, int core, int order, int mem,
                      int n, float* x, float* y, const float* s, const float* r, float* u, float* v,
                      int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
                      const float* pvs, const float* pss, double fsx, double fsy, double dt, int nsteps);
+
+/*
+ * One convection step of a flow WITH bodies, particles resident on the GPU across all Runge-Kutta stages.
+ *
+ * The reference's stage is find_derivs = solve_bem -> find_vels (src/Convection.h:229-243) followed by
+ * ElementBase::move and clear_inner_layer (:303-307, :334, :388-391, :489-578).  solve_bem's linear solve belongs
+ * to the host application (Eigen GMRES, src/BEM.h:166-232); everything around it is done here:
+ *   per stage   zero_vels + points_affect_panels + Surfaces::finalize_vels(fs) on the panels (src/BEMHelper.h:88-100)
+ *               -> `solve` (host callback: right-hand side, linear solve, new sheet strengths)
+ *               -> find_vels of the particles on themselves with the new strengths -> move -> clear_inner_layer(1, ...)
+ * so a step costs ONE upload and ONE download of the particle arrays plus, per stage, 2*Np floats each way.
+ *
+ *   solve(user, stage, time, np, pu, pv, vs, ss): pu,pv = finalised particle-induced velocity at the panel centres
+ *       (what Surfaces::get_vel holds when the reference calls vels_to_rhs_panels); writes the new vortex strengths to
+ *       vs[np] and -- when the caller passed pss != NULL -- the source strengths to ss[np]; returns 0 on success.
+ *       vs/ss are the caller's own pvs/pss arrays, so after the call they hold the strengths of the last stage.
+ *       stage = 0, 1, 2; time = the stage time the reference passes to solve_bem.
+ *   area, snx, sny: panel lengths and unit normals (Surfaces::get_area / get_norm); cutoff_mult = 0.5/sqrt(2 pi) and
+ *       ips as for o2d_clear_inner_layer.  Bodies do not move inside a step (fixed or externally transformed panels).
+ * Host arrays only (the callback runs on the host).  x,y are advanced in place; u,v as for o2d_advect.
+ */
+typedef int (*o2d_bem_solve_fn)(void* user, int stage, double time, int np, const float* pu, const float* pv,
+                                float* vs, float* ss);
+int o2d_advect_bodies(o2d_context* ctx, int core, int order, int mem,
+                      int n, float* x, float* y, const float* s, const float* r, float* u, float* v,
+                      int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                      const float* area, const float* snx, const float* sny, float* pvs, float* pss,
+                      double fsx, double fsy, double time, double dt, float cutoff_mult, float ips,
+                      o2d_bem_solve_fn solve, void* user);
 
 /*
  * Surfaces::add_solved_rot_strengths / add_rot_strengths_base (reference src/Surfaces.h:556-620), which

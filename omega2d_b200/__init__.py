@@ -31,6 +31,26 @@ OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE, ERR_COMM = 0, -1, -2,
 
 _fp = C.POINTER(C.c_float)
 _up = C.POINTER(C.c_uint32)
+# o2d_bem_solve_fn (include/omega2d_b200.h): int solve(user, stage, time, np, pu, pv, vs, ss)
+BEM_SOLVE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_int, _fp, _fp, _fp, _fp)
+
+
+def bem_solve_callback(fn):
+    """Wrap fn(stage, time, pu, pv) -> (vs, ss|None) (numpy float32 arrays) as an o2d_bem_solve_fn."""
+    def trampoline(user, stage, time, npan, pu, pv, vs, ss):
+        try:
+            a = np.ctypeslib.as_array(pu, shape=(npan,)).copy()
+            b = np.ctypeslib.as_array(pv, shape=(npan,)).copy()
+            nvs, nss = fn(int(stage), float(time), a, b)
+            np.ctypeslib.as_array(vs, shape=(npan,))[:] = np.asarray(nvs, np.float32)
+            if ss and nss is not None:
+                np.ctypeslib.as_array(ss, shape=(npan,))[:] = np.asarray(nss, np.float32)
+            return 0
+        except Exception:   # never let an exception cross the C boundary
+            import traceback
+            traceback.print_exc()
+            return 1
+    return BEM_SOLVE_FN(trampoline)
 
 
 class O2DError(RuntimeError):
@@ -80,6 +100,8 @@ def load_library() -> C.CDLL:
                                   i, vp, vp, vp, vp, vp, vp, d, d]
     lib.o2d_advect.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, d, d, d]
     lib.o2d_advect_steps.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, d, d, d, i]
+    lib.o2d_advect_bodies.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp,
+                                      d, d, d, d, C.c_float, C.c_float, BEM_SOLVE_FN, vp]
     lib.o2d_panels_on_panels_coeff.argtypes = [vp, i, i, i, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp,
                                                i, i, C.c_longlong, vp]
     lib.o2d_clear_inner_layer.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp, i, vp, vp, C.c_float, C.c_float,
@@ -460,6 +482,28 @@ class Context:
         u, v = np.empty(x.size, np.float32), np.empty(x.size, np.float32)
         self.advect(core, order, MEM_HOST, x.size, x, y, s, r, u, v, npan, nn, nx, ny, idx, pvs, pss, fs, dt)
         return x, y, u, v
+
+    def advect_bodies_np(self, core, order, x, y, s, r, panels, area, normals, solve, dt, ips, fs=(0.0, 0.0), time=0.0,
+                         cutoff_mult=None):
+        """One convection step with bodies (o2d_advect_bodies).  panels = (nx, ny, idx, vs, ss|None); normals = (snx, sny);
+        solve(stage, time, pu, pv) -> (vs, ss).  Returns (x, y, u, v, vs, ss) after the step."""
+        core = CORE_ID[core] if isinstance(core, str) else int(core)
+        x, y = np.array(x, np.float32), np.array(y, np.float32)
+        s, r, area = map(_f32, (s, r, area))
+        nx, ny = map(_f32, panels[:2])
+        idx = np.ascontiguousarray(panels[2], dtype=np.uint32)
+        pvs = np.array(panels[3], np.float32)
+        pss = None if panels[4] is None else np.array(panels[4], np.float32)
+        snx, sny = map(_f32, normals)
+        u, v = np.empty(x.size, np.float32), np.empty(x.size, np.float32)
+        if cutoff_mult is None:
+            cutoff_mult = np.float32(0.5 / np.sqrt(2.0 * np.pi))   # src/Convection.h:306
+        cb = bem_solve_callback(solve)
+        self._check(self.lib.o2d_advect_bodies(
+            self._h, core, int(order), MEM_HOST, x.size, _ptr(x), _ptr(y), _ptr(s), _ptr(r), _ptr(u), _ptr(v),
+            pvs.size, nx.size, _ptr(nx), _ptr(ny), _ptr(idx), _ptr(area), _ptr(snx), _ptr(sny), _ptr(pvs), _ptr(pss),
+            float(fs[0]), float(fs[1]), float(time), float(dt), float(cutoff_mult), float(ips), cb, None))
+        return x, y, u, v, pvs, pss
 
     def panels_on_panels_coeff_np(self, src, sarea, targ, tbases, both=True, same=False, ld=None):
         """src/targ = (nx, ny, idx); tbases = (ttx, tty, tnx, tny, tarea).  Returns (cols, ld) float32."""

@@ -526,7 +526,7 @@ static int points_on_panels_impl(o2d_context* c, int ns, const float* sx, const 
     CU(c->packed.reserve((size_t)ns_padded * 16));
     CU(launch_pack_sources(101, ns, sx, sy, ss, nullptr, c->packed.as<float4>(), ns_padded, c->stream));
     c->launches++;
-    const int nb = (np + 63) / 64;
+    const int nb = (np + ptpan_block_panels() - 1) / ptpan_block_panels();
     const int slots = c->sm_count * ptpan_occupancy();
     nchunks = choose_chunks(nb, ntiles, slots, 4096);
     a.packed_src = c->packed.as<float4>();

@@ -115,3 +115,7 @@ int o2d_panels_on_points_device(o2d_context* c, int np, const float* nx, const f
 int o2d_points_on_panels_device(o2d_context* c, int ns, const float* sx, const float* sy, const float* ss,
                                 int np, const float* nx, const float* ny, const uint32_t* idx,
                                 const float* area, float* pu, float* pv);
+// clear_inner_layer push (mode 1) / reflect_interior (mode 2) on device arrays; d_moved may be nullptr
+int o2d_cil_device(o2d_context* c, int mode, int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                   const float* snx, const float* sny, int n, float* tx, float* ty, float cutoff_mult, float ips,
+                   unsigned long long* d_moved);

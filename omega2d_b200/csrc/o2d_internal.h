@@ -142,6 +142,7 @@ cudaError_t launch_ptpan_combine_geom(const double* partial, int nchunks, const 
 cudaError_t launch_ptpan_reduce_chunks(const double* partial, int nchunks, int np, double* out, cudaStream_t st);
 int panels_occupancy(int rpt);
 int ptpan_occupancy();
+int ptpan_block_panels();   // panels per CTA of points_on_panels_kernel
 
 // elementwise helpers
 cudaError_t launch_zero(int n, float* u, float* v, float* w, float* e, cudaStream_t st);

@@ -188,68 +188,92 @@ int panels_occupancy(int rpt) {
 }
 
 // ---- points on panels (reciprocity) ----------------------------------------------------------------------
-constexpr int kPtPanThreads = 64;
+// 128 threads x 2 panels per thread: a staged particle pair is read once (two LDS.128) for two panels, and the two
+// independent series evaluations per thread keep the FMA pipe fed (one panel per thread on 64-thread CTAs held 16
+// warps per SM at 76 % FMA-pipe activity).
+constexpr int kPtPanThreads = 128;
+constexpr int kPtPanPPT = 2;
 
 __global__ void __launch_bounds__(kPtPanThreads)
 points_on_panels_kernel(const PtPanArgs a) {
   __shared__ float4 s[kTile];   // one tile of packed particle pairs (16 KiB)
   const int tid = threadIdx.x;
-  const int i = blockIdx.x * kPtPanThreads + tid;
-  const bool ok = i < a.np;
-  float x0 = 1.0e6f, y0 = 1.0e6f, px = 1.0f, py = 0.0f;
-  if (ok) {
-    const uint32_t i0 = a.idx[2 * i], i1 = a.idx[2 * i + 1];
-    x0 = a.nx[i0]; y0 = a.ny[i0];
-    px = a.nx[i1] - x0; py = a.ny[i1] - y0;
+  float x0[kPtPanPPT], y0[kPtPanPPT], px[kPtPanPPT], py[kPtPanPPT], thr[kPtPanPPT];
+  float2 Hx[kPtPanPPT], Hy[kPtPanPPT];
+  bool ok[kPtPanPPT];
+#pragma unroll
+  for (int k = 0; k < kPtPanPPT; ++k) {
+    const int i = (blockIdx.x * kPtPanPPT + k) * kPtPanThreads + tid;
+    ok[k] = i < a.np;
+    x0[k] = 1.0e6f; y0[k] = 1.0e6f; px[k] = 1.0f; py[k] = 0.0f;
+    if (ok[k]) {
+      const uint32_t i0 = a.idx[2 * i], i1 = a.idx[2 * i + 1];
+      x0[k] = a.nx[i0]; y0[k] = a.ny[i0];
+      px[k] = a.nx[i1] - x0[k]; py[k] = a.ny[i1] - y0[k];
+    }
+    // far-field form (panel_far2) with the roles mirrored: e' = centre - t = (node0 - t) + p/2 and H' = +p/2 give
+    // the same zeta'; a packed lane pair is TWO PARTICLES against this thread's panel
+    Hx[k] = f2(0.5f * px[k]); Hy[k] = f2(0.5f * py[k]);
+    thr[k] = (Hx[k].x * Hx[k].x + Hy[k].x * Hy[k].x) * (1.0f / kFarZeta2);
   }
   const int tile_begin = blockIdx.y * a.tiles_per_chunk;
   const int tile_end = min(tile_begin + a.tiles_per_chunk, a.ntiles);
-  // far-field form (panel_far2) with the roles mirrored: e' = centre - t = (node0 - t) + p/2 and H' = +p/2 give
-  // the same zeta'; a packed lane pair is TWO PARTICLES against this thread's panel
-  const float2 Hx = f2(0.5f * px), Hy = f2(0.5f * py);
-  const float thr = (Hx.x * Hx.x + Hy.x * Hy.x) * (1.0f / kFarZeta2);
-  double acc1 = 0.0, acc2 = 0.0;
+  double acc1[kPtPanPPT], acc2[kPtPanPPT];
+#pragma unroll
+  for (int k = 0; k < kPtPanPPT; ++k) { acc1[k] = 0.0; acc2[k] = 0.0; }
   for (int t = tile_begin; t < tile_end; ++t) {
     __syncthreads();
     const float4* g = a.packed_src + (size_t)t * kTile;
     for (int k = tid; k < kTile; k += kPtPanThreads) s[k] = g[k];
     __syncthreads();
-    float2 p1 = f2(0.0f), p2 = f2(0.0f);
+    float2 p1[kPtPanPPT], p2[kPtPanPPT];
+#pragma unroll
+    for (int k = 0; k < kPtPanPPT; ++k) { p1[k] = f2(0.0f); p2[k] = f2(0.0f); }
 #pragma unroll 2
     for (int p = 0; p < kTile / 2; ++p) {
       const float4 A = s[2 * p];      // -x0 -x1 -y0 -y1 of two particles
       const float4 B = s[2 * p + 1];  // s0 s1 . .
-      const float2 ex = add2(add2(f2(A.x, A.y), f2(x0)), Hx);
-      const float2 ey = add2(add2(f2(A.z, A.w), f2(y0)), Hy);
-      float2 rr, ri, e2;
-      panel_far2(ex, ey, Hx, Hy, rr, ri, e2);
-      const bool na = !(e2.x > thr), nb = !(e2.y > thr);
-      if (__any_sync(0xffffffffu, na || nb)) {
-        float us, vs;
-        panel_pair(x0, y0, px, py, -A.x, -A.z, us, vs);
-        if (na) { ri.x = -0.5f * us; rr.x = -0.5f * vs; }
-        panel_pair(x0, y0, px, py, -A.y, -A.w, us, vs);
-        if (nb) { ri.y = -0.5f * us; rr.y = -0.5f * vs; }
-      }
       const float2 S = f2(B.x, B.y);
-      p1 = fma2(S, ri, p1);
-      p2 = fma2(S, rr, p2);
+#pragma unroll
+      for (int k = 0; k < kPtPanPPT; ++k) {
+        const float2 ex = add2(add2(f2(A.x, A.y), f2(x0[k])), Hx[k]);
+        const float2 ey = add2(add2(f2(A.z, A.w), f2(y0[k])), Hy[k]);
+        float2 rr, ri, e2;
+        panel_far2(ex, ey, Hx[k], Hy[k], rr, ri, e2);
+        const bool na = !(e2.x > thr[k]), nb = !(e2.y > thr[k]);
+        if (__any_sync(0xffffffffu, na || nb)) {
+          float us, vs;
+          panel_pair(x0[k], y0[k], px[k], py[k], -A.x, -A.z, us, vs);
+          if (na) { ri.x = -0.5f * us; rr.x = -0.5f * vs; }
+          panel_pair(x0[k], y0[k], px[k], py[k], -A.y, -A.w, us, vs);
+          if (nb) { ri.y = -0.5f * us; rr.y = -0.5f * vs; }
+        }
+        p1[k] = fma2(S, ri, p1[k]);
+        p2[k] = fma2(S, rr, p2[k]);
+      }
     }
-    acc1 += -2.0 * ((double)p1.x + (double)p1.y);
-    acc2 += -2.0 * ((double)p2.x + (double)p2.y);
+#pragma unroll
+    for (int k = 0; k < kPtPanPPT; ++k) {
+      acc1[k] += -2.0 * ((double)p1[k].x + (double)p1[k].y);
+      acc2[k] += -2.0 * ((double)p2[k].x + (double)p2[k].y);
+    }
   }
-  if (!ok) return;
-  if (a.partial == nullptr) {
-    const double mult = 1.0 / sqrt((double)px * px + (double)py * py);
-    const double U = (acc1 * px - acc2 * py) * mult;
-    const double V = (acc1 * py + acc2 * px) * mult;
-    const double plen = 1.0 / (double)a.area[i];       // src/Influence.h:727
-    a.pu[i] = (float)((double)a.pu[i] - plen * U);      // src/Influence.h:758-759
-    a.pv[i] = (float)((double)a.pv[i] - plen * V);
-  } else {
-    double* dst = a.partial + ((size_t)blockIdx.y * 2) * (size_t)a.np + i;
-    dst[0] = acc1;
-    dst[a.np] = acc2;
+#pragma unroll
+  for (int k = 0; k < kPtPanPPT; ++k) {
+    if (!ok[k]) continue;
+    const int i = (blockIdx.x * kPtPanPPT + k) * kPtPanThreads + tid;
+    if (a.partial == nullptr) {
+      const double mult = 1.0 / sqrt((double)px[k] * px[k] + (double)py[k] * py[k]);
+      const double U = (acc1[k] * px[k] - acc2[k] * py[k]) * mult;
+      const double V = (acc1[k] * py[k] + acc2[k] * px[k]) * mult;
+      const double plen = 1.0 / (double)a.area[i];       // src/Influence.h:727
+      a.pu[i] = (float)((double)a.pu[i] - plen * U);      // src/Influence.h:758-759
+      a.pv[i] = (float)((double)a.pv[i] - plen * V);
+    } else {
+      double* dst = a.partial + ((size_t)blockIdx.y * 2) * (size_t)a.np + i;
+      dst[0] = acc1[k];
+      dst[a.np] = acc2[k];
+    }
   }
 }
 
@@ -277,7 +301,7 @@ ptpan_combine_kernel(const double* __restrict__ partial, int nchunks, int np,
 }
 
 cudaError_t launch_points_on_panels(const PtPanArgs& a, int nchunks, cudaStream_t st) {
-  dim3 grid((a.np + kPtPanThreads - 1) / kPtPanThreads, nchunks, 1);
+  dim3 grid((a.np + kPtPanThreads * kPtPanPPT - 1) / (kPtPanThreads * kPtPanPPT), nchunks, 1);
   points_on_panels_kernel<<<grid, kPtPanThreads, 0, st>>>(a);
   return cudaGetLastError();
 }
@@ -299,6 +323,7 @@ cudaError_t launch_ptpan_reduce_chunks(const double* partial, int nchunks, int n
   ptpan_reduce_chunks_kernel<<<(2 * np + 255) / 256, 256, 0, st>>>(partial, nchunks, np, out);
   return cudaGetLastError();
 }
+int ptpan_block_panels() { return kPtPanThreads * kPtPanPPT; }
 int ptpan_occupancy() {
   int nb = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, points_on_panels_kernel, kPtPanThreads, 0) != cudaSuccess) return 1;

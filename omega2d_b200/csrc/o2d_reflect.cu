@@ -247,9 +247,9 @@ clear_inner_kernel(const CilArgs a) {
 
 }  // namespace
 
-static int cil_device(o2d_context* c, int mode, int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
-                      const float* snx, const float* sny, int n, float* tx, float* ty, float cutoff_mult, float ips,
-                      unsigned long long* d_moved) {
+int o2d_cil_device(o2d_context* c, int mode, int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                   const float* snx, const float* sny, int n, float* tx, float* ty, float cutoff_mult, float ips,
+                   unsigned long long* d_moved) {
   // scratch: node normals (2*nnodes floats) + packed panels (3 float4 each) + group bounds (1 float4 per 32 panels)
   const size_t nn_bytes = ((2 * (size_t)nnodes * sizeof(float) + 255) / 256) * 256;
   const int ngroups = (np + kCilGroup - 1) / kCilGroup;
@@ -296,7 +296,7 @@ static int cil_entry(o2d_context* c, int mode, int mem,
   CU(cudaMemsetAsync(d_moved, 0, sizeof(unsigned long long), c->stream));
   int rc;
   if (mem == O2D_MEM_DEVICE) {
-    if ((rc = cil_device(c, mode, np, nnodes, nx, ny, idx, snx, sny, n, tx, ty, cutoff_mult, ips, d_moved))) return rc;
+    if ((rc = o2d_cil_device(c, mode, np, nnodes, nx, ny, idx, snx, sny, n, tx, ty, cutoff_mult, ips, d_moved))) return rc;
     if (num_moved) {   // the count is the only thing that needs the host: synchronous only when asked for
       unsigned long long h = 0;
       CU(cudaMemcpyAsync(&h, d_moved, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
@@ -317,7 +317,7 @@ static int cil_entry(o2d_context* c, int mode, int mem,
       (rc = o2d_h2d(c, dsny, sny, np)) || (rc = o2d_h2d(c, dtx, tx, n)) || (rc = o2d_h2d(c, dty, ty, n)))
     return rc;
   if (int rc_ = o2d_h2d_bytes(c, c->hidx.p, idx, (size_t)2 * np * sizeof(uint32_t))) return rc_;
-  if ((rc = cil_device(c, mode, np, nnodes, dnx, dny, c->hidx.as<uint32_t>(), dsnx, dsny, n, dtx, dty, cutoff_mult, ips, d_moved)))
+  if ((rc = o2d_cil_device(c, mode, np, nnodes, dnx, dny, c->hidx.as<uint32_t>(), dsnx, dsny, n, dtx, dty, cutoff_mult, ips, d_moved)))
     return rc;
   unsigned long long h = 0;
   if ((rc = o2d_d2h(c, tx, dtx, n)) || (rc = o2d_d2h(c, ty, dty, n))) return rc;

@@ -11,6 +11,7 @@
 #include "o2d_context.h"
 
 #include <cmath>
+#include <vector>
 
 using namespace o2d;
 
@@ -349,4 +350,156 @@ extern "C" int o2d_advect(o2d_context* c, int core, int order, int mem,
                           int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
                           const float* pvs, const float* pss, double fsx, double fsy, double dt) {
   return o2d_advect_steps(c, core, order, mem, n, x, y, s, r, u, v, np, nnodes, nx, ny, idx, pvs, pss, fsx, fsy, dt, 1);
+}
+
+// ---- convection step of a flow WITH bodies ---------------------------------------------------------------------
+// The reference's find_derivs is  solve_bem -> find_vels  (src/Convection.h:229-243), and after every move of every
+// Runge-Kutta stage it runs clear_inner_layer (:303-307,:334,:388-391,:489-578).  solve_bem's linear solve is the
+// host application's (Eigen GMRES, src/BEM.h:166-232), but everything around it is on the path: the right-hand side
+// is the particle-induced velocity at the panel centres (points_affect_panels + Surfaces::finalize_vels,
+// src/BEMHelper.h:88-100), the solved strengths feed panels_affect_points, and the particles are then moved and
+// pushed out of the body.  Here the particles stay on the GPU for the whole step; per stage only 2*Np floats go to
+// the host (the panel velocities, for the caller's `solve`) and 2*Np come back (the sheet strengths).
+namespace {
+
+struct BodyDev {
+  Panels pan;                 // geometry + strengths (device)
+  const float* area = nullptr;
+  const float* snx = nullptr;
+  const float* sny = nullptr;
+  float* vs = nullptr;        // strengths, rewritten after every solve
+  float* ss = nullptr;
+  float* pu = nullptr;        // panel-centre velocities
+  float* pv = nullptr;
+  int nnodes = 0;
+};
+
+int stage_derivs(o2d_context* c, int core, int n, const float* x, const float* y, const float* s, const float* r,
+                 float* u, float* v, BodyDev& b, float* h_pu, float* h_pv, float* h_vs, float* h_ss,
+                 double fsx, double fsy, int stage, double time, o2d_bem_solve_fn solve, void* user) {
+  const int np = b.pan.np;
+  int rc;
+  // solve_bem, right-hand side: zero_vels; points_affect_panels; finalize_vels(fs)  (src/BEMHelper.h:88-100)
+  CU(launch_zero(np, b.pu, b.pv, nullptr, nullptr, c->stream));
+  c->launches++;
+  if ((rc = o2d_points_on_panels_device(c, n, x, y, s, np, b.pan.nx, b.pan.ny, b.pan.idx, b.area, b.pu, b.pv))) return rc;
+  CU(launch_finalize(np, b.pu, b.pv, nullptr, nullptr, fsx, fsy, c->stream));
+  c->launches++;
+  CU(cudaMemcpyAsync(h_pu, b.pu, (size_t)np * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(h_pv, b.pv, (size_t)np * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  // the caller's BEM: RHS from these velocities, linear solve, new sheet strengths
+  if (int urc = solve(user, stage, time, np, h_pu, h_pv, h_vs, h_ss))
+    return fail(O2D_ERR_INVALID, "o2d_advect_bodies: the solve callback returned %d at stage %d", urc, stage);
+  CU(cudaMemcpyAsync(b.vs, h_vs, (size_t)np * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  if (b.ss) CU(cudaMemcpyAsync(b.ss, h_ss, (size_t)np * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  // find_vels(fs, vort, bdry, vort)
+  return find_vels_device(c, core, RES_U, n, x, y, s, r, b.pan, n, x, y, r, u, v, nullptr, fsx, fsy);
+}
+
+}  // namespace
+
+extern "C" int o2d_advect_bodies(o2d_context* c, int core, int order, int mem,
+                                 int n, float* x, float* y, const float* s, const float* r, float* u, float* v,
+                                 int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                                 const float* area, const float* snx, const float* sny, float* pvs, float* pss,
+                                 double fsx, double fsy, double time, double dt, float cutoff_mult, float ips,
+                                 o2d_bem_solve_fn solve, void* user) {
+  if (int rc = o2d_check_common(c, mem)) return rc;
+  if (mem != O2D_MEM_HOST)
+    return fail(O2D_ERR_UNSUPPORTED, "o2d_advect_bodies takes host arrays (the solve callback runs on the host every stage)");
+  if (core < 0 || core > 4) return fail(O2D_ERR_INVALID, "unknown core %d", core);
+  if (order < 1 || order > 3)
+    return fail(O2D_ERR_INVALID, "Convection integrator orders over 3 unsupported (reference src/Convection.h:259)");
+  if (n < 0) return fail(O2D_ERR_INVALID, "negative count");
+  if (np <= 0) return fail(O2D_ERR_INVALID, "o2d_advect_bodies needs a surface collection (particle-only flows: o2d_advect)");
+  if (int rc = check_panels(np, nnodes, nx, ny, idx, pvs)) return rc;
+  if (!area || !snx || !sny || !solve) return fail(O2D_ERR_INVALID, "NULL panel array or callback");
+  if (n == 0) return O2D_OK;
+  if (!x || !y || !s || !r || !u || !v) return fail(O2D_ERR_INVALID, "NULL particle array");
+  for (int k = 0; k < 2 * np; ++k)
+    if (idx[k] >= (uint32_t)nnodes) return fail(O2D_ERR_INVALID, "panel node index %u out of range", idx[k]);
+  int rc;
+  // ---- one upload: particles and the panel description -------------------------------------------------------------
+  CU(c->hsrc.reserve(4 * padded_floats(n) + 256));
+  CU(c->hout.reserve(kMaxOut * padded_floats(n)));
+  CU(c->adv.reserve(8 * padded_floats(n)));
+  CU(c->hpan.reserve(2 * padded_floats(nnodes) + 7 * padded_floats(np)));
+  CU(c->hidx.reserve((size_t)2 * np * sizeof(uint32_t)));
+  Stager S(c, &c->hsrc), O(c, &c->hout), A(c, &c->adv), Pn(c, &c->hpan);
+  float *dx = S.take(n), *dy = S.take(n), *ds = S.take(n), *dr = S.take(n);
+  float *du = O.take(n), *dv = O.take(n);
+  float *x1 = A.take(n), *y1 = A.take(n), *u1 = A.take(n), *v1 = A.take(n);
+  float *x2 = A.take(n), *y2 = A.take(n), *u2 = A.take(n), *v2 = A.take(n);
+  float *dnx = Pn.take(nnodes), *dny = Pn.take(nnodes);
+  BodyDev b;
+  b.vs = Pn.take(np); b.ss = pss ? Pn.take(np) : nullptr;
+  float *darea = Pn.take(np), *dsnx = Pn.take(np), *dsny = Pn.take(np);
+  b.pu = Pn.take(np); b.pv = Pn.take(np);
+  if ((rc = o2d_h2d(c, dx, x, n)) || (rc = o2d_h2d(c, dy, y, n)) || (rc = o2d_h2d(c, ds, s, n)) || (rc = o2d_h2d(c, dr, r, n)) ||
+      (rc = o2d_h2d(c, dnx, nx, nnodes)) || (rc = o2d_h2d(c, dny, ny, nnodes)) || (rc = o2d_h2d(c, darea, area, np)) ||
+      (rc = o2d_h2d(c, dsnx, snx, np)) || (rc = o2d_h2d(c, dsny, sny, np)))
+    return rc;
+  if ((rc = o2d_h2d_bytes(c, c->hidx.p, idx, (size_t)2 * np * sizeof(uint32_t)))) return rc;
+  b.pan.np = np; b.pan.nx = dnx; b.pan.ny = dny; b.pan.idx = c->hidx.as<uint32_t>(); b.pan.vs = b.vs; b.pan.ss = b.ss;
+  b.area = darea; b.snx = dsnx; b.sny = dsny; b.nnodes = nnodes;
+  // host side of the per-stage exchange: 2*Np floats out, 2*Np back (pinned when the context has the room)
+  std::vector<float> hbuf;
+  float* h_pu; float* h_pv;
+  const size_t need = 2 * (size_t)np * sizeof(float);
+  if (c->pin && c->pin_off + need + 128 <= c->pin_cap) {
+    h_pu = reinterpret_cast<float*>(c->pin + ((c->pin_off + 63) / 64) * 64);
+    h_pv = h_pu + np;
+    c->pin_off = ((c->pin_off + 63) / 64) * 64 + need;
+  } else {
+    hbuf.resize(2 * (size_t)np);
+    h_pu = hbuf.data(); h_pv = h_pu + np;
+  }
+  const int nb = (n + 255) / 256;
+  const float fdt = (float)dt;   // "(S)_dt" in ElementBase::move
+  auto derivs = [&](int stage, double t, const float* px, const float* py, float* pu_, float* pv_) {
+    return stage_derivs(c, core, n, px, py, ds, dr, pu_, pv_, b, h_pu, h_pv, pvs, pss, fsx, fsy, stage, t, solve, user);
+  };
+  auto clear = [&](float* px, float* py) {
+    return o2d_cil_device(c, 1, np, nnodes, dnx, dny, b.pan.idx, dsnx, dsny, n, px, py, cutoff_mult, ips, nullptr);
+  };
+  if ((rc = derivs(0, time, dx, dy, du, dv))) return rc;
+  if (order == 1) {
+    // advect_1st (src/Convection.h:277-308)
+    move1_kernel<<<nb, 256, 0, c->stream>>>(n, dx, dy, dx, dy, du, dv, fdt, 1.0);
+    CU(cudaGetLastError());
+    c->launches++;
+    if ((rc = clear(dx, dy))) return rc;
+  } else if (order == 2) {
+    // advect_2nd_ralston (src/Convection.h:314-392)
+    const double twothirds = 2.0 / 3.0;
+    move1_kernel<<<nb, 256, 0, c->stream>>>(n, dx, dy, x1, y1, du, dv, (float)(twothirds * dt), 1.0);
+    CU(cudaGetLastError());
+    c->launches++;
+    if ((rc = clear(x1, y1))) return rc;
+    if ((rc = derivs(1, time + twothirds * dt, x1, y1, u1, v1))) return rc;
+    move23_kernel<<<nb, 256, 0, c->stream>>>(n, dx, dy, du, dv, u1, v1, nullptr, nullptr, fdt, 0.25, 0.75, 0.0);
+    CU(cudaGetLastError());
+    c->launches++;
+    if ((rc = clear(dx, dy))) return rc;
+  } else {
+    // advect_3rd (src/Convection.h:472-595)
+    move1_kernel<<<nb, 256, 0, c->stream>>>(n, dx, dy, x1, y1, du, dv, (float)(0.5 * dt), 1.0);
+    CU(cudaGetLastError());
+    if ((rc = clear(x1, y1))) return rc;
+    if ((rc = derivs(1, time + 0.5 * dt, x1, y1, u1, v1))) return rc;
+    move1_kernel<<<nb, 256, 0, c->stream>>>(n, dx, dy, x2, y2, u1, v1, (float)(0.75 * dt), 1.0);
+    CU(cudaGetLastError());
+    if ((rc = clear(x2, y2))) return rc;
+    if ((rc = derivs(2, time + 0.75 * dt, x2, y2, u2, v2))) return rc;
+    move23_kernel<<<nb, 256, 0, c->stream>>>(n, dx, dy, du, dv, u1, v1, u2, v2, fdt, 2.0 / 9.0, 3.0 / 9.0, 4.0 / 9.0);
+    CU(cudaGetLastError());
+    c->launches += 3;
+    if ((rc = clear(dx, dy))) return rc;
+  }
+  // ---- one download -------------------------------------------------------------------------------------------------------
+  if ((rc = o2d_d2h(c, x, dx, n)) || (rc = o2d_d2h(c, y, dy, n)) || (rc = o2d_d2h(c, u, du, n)) || (rc = o2d_d2h(c, v, dv, n)))
+    return rc;
+  if (int rc_ = o2d_finish_host(c)) return rc_;
+  return O2D_OK;
 }

@@ -414,6 +414,28 @@ class Ref:
                float(fs[0]), float(fs[1]), float(dt))
         assert rc == 0
         return x, y, u, v
+    def advect_bodies(self, order, x, y, s, r, panels, solve, dt, ips, fs=(0.0, 0.0), time=0.0):
+        """The reference's convection step with bodies (orchestration restated in ref_driver.cpp around the reference's own
+        points_affect_panels / finalize_vels / find_vels pieces / Points::move / clear_inner_layer); the BEM linear solve is
+        the caller's solve(stage, time, pu, pv) -> (vs, ss).  Returns (x, y, u, v, vs, ss)."""
+        from omega2d_b200 import bem_solve_callback
+        x, y = np.array(x, np.float32), np.array(y, np.float32)
+        s, r = map(_f32, (s, r))
+        nx, ny = map(_f32, panels[:2])
+        idx = np.ascontiguousarray(panels[2], dtype=np.uint32)
+        vs = np.array(panels[3], np.float32)
+        ss = None if panels[4] is None else np.array(panels[4], np.float32)
+        u, v = np.zeros(x.size, np.float32), np.zeros(x.size, np.float32)
+        cb = bem_solve_callback(solve)
+        f = self.lib.o2dref_advect_bodies
+        f.argtypes = [C.c_int, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, _fp, _fp, _up, _fp, _fp,
+                      C.c_double, C.c_double, C.c_double, C.c_double, C.c_float, C.c_void_p, C.c_void_p]
+        rc = f(int(order), int(x.size), _f(x), _f(y), _f(s), _f(r), _f(u), _f(v), int(vs.size), int(nx.size), _f(nx), _f(ny),
+               _u(idx), _f(vs), _f(ss), float(fs[0]), float(fs[1]), float(time), float(dt), float(ips),
+               C.cast(cb, C.c_void_p), None)
+        assert rc == 0, rc
+        return x, y, u, v, vs, ss
+
     def panels_on_panels_coeff(self, src, targ=None):
         """The reference's own panels_on_panels_coeff<float> (always both strengths).  Returns
         (coeffs as (2*ns, 2*nt) array, (ttx, tty, tnx, tny, tarea), sarea)."""

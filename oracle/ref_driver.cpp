@@ -357,6 +357,82 @@ int o2dref_advect(int order, int n, float* x, float* y, const float* s, const fl
 }
 
 
+// ---- the convection step of a flow with bodies ---------------------------------------------------------------
+// advect_1st / advect_2nd_ralston / advect_3rd (src/Convection.h:277-595) WITH the per-stage solve_bem and
+// clear_inner_layer.  Restated orchestration (Convection.h / BEMHelper.h need Eigen) around the reference's own
+// pieces: for solve_bem (src/BEMHelper.h:43-260) the right-hand-side part -- zero_vels, InfluenceVisitor
+// (points_affect_panels), Surfaces::finalize_vels -- runs on the reference's own Surfaces; the linear solve itself
+// (BEM::solve, Eigen) is replaced by the caller's `solve` callback, which receives those panel velocities and returns
+// the sheet strengths that the reference would copy back with set_str (:237-254); then the reference's find_vels
+// orchestration, Points::move and clear_inner_layer<float>(1, ...) (src/Reflect.h:735-768).
+typedef int (*bem_solve_fn)(void* user, int stage, double time, int np, const float* pu, const float* pv, float* vs, float* ss);
+
+static int ref_derivs(const std::array<double,Dimensions>& fs, std::vector<Collection>& vort, std::vector<Collection>& bdry,
+                      int stage, double time, bem_solve_fn solve, void* user, float* vs, float* ss) {
+  InfluenceVisitor<float,double> ivisitor = {ResultsType(velonly), ExecEnv(true, direct, cpu_x86)};
+  Surfaces<float>& surf = std::get<Surfaces<float>>(bdry[0]);
+  const int np = (int)surf.get_npanels();
+  surf.zero_vels();
+  for (auto& src : vort) std::visit(ivisitor, src, bdry[0]);
+  surf.finalize_vels(fs);
+  const auto& pu = surf.get_vel();
+  std::vector<float> hu(pu[0].begin(), pu[0].end()), hv(pu[1].begin(), pu[1].end());
+  if (int rc = solve(user, stage, time, np, hu.data(), hv.data(), vs, ss)) return rc;
+  auto& gv = surf.get_vort_str();
+  for (int i = 0; i < np; ++i) gv[i] = vs[i];
+  if (ss) { auto& gs = surf.get_src_str(); for (int i = 0; i < np; ++i) gs[i] = ss[i]; }
+  ref_find_vels(fs, vort, bdry, vort, velonly);
+  return 0;
+}
+
+int o2dref_advect_bodies(int order, int n, float* x, float* y, const float* s, const float* r, float* u, float* v,
+                         int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx, float* vs, float* ss,
+                         double fsx, double fsy, double time, double dt, float ips, bem_solve_fn solve, void* user) {
+  if (order < 1 || order > 3 || np <= 0) return -1;
+  StdoutMute mute;
+  const std::array<double,Dimensions> fs = {fsx, fsy};
+  const float cutoff = 0.5/std::sqrt(2.0*M_PI);
+  std::vector<Collection> vort, bdry;
+  vort.push_back(make_points(n, x, y, s, r));
+  bdry.push_back(make_surfaces(np, nnodes, nx, ny, idx, vs, ss));
+  if (ref_derivs(fs, vort, bdry, 0, time, solve, user, vs, ss)) return -2;
+  if (order == 1) {
+    for (auto& coll : vort) std::visit([=](auto& elem) { elem.move(time, dt, 1.0, elem); }, coll);
+    clear_inner_layer<float>(1, bdry, vort, cutoff, ips);
+  } else if (order == 2) {
+    const double twothirds = 2.0/3.0;
+    std::vector<Collection> interim = vort;
+    for (auto& coll : interim) std::visit([=](auto& elem) { elem.move(time, twothirds*dt, 1.0, elem); }, coll);
+    clear_inner_layer<float>(1, bdry, interim, cutoff, ips);
+    if (ref_derivs(fs, interim, bdry, 1, time + twothirds*dt, solve, user, vs, ss)) return -2;
+    Points<float>& p1 = std::get<Points<float>>(vort[0]);
+    Points<float>& p2 = std::get<Points<float>>(interim[0]);
+    p1.move(time, dt, 0.25, p1, 0.75, p2);
+    clear_inner_layer<float>(1, bdry, vort, cutoff, ips);
+  } else {
+    std::vector<Collection> vort1 = vort;
+    for (auto& coll : vort1) std::visit([=](auto& elem) { elem.move(time, 0.5*dt, 1.0, elem); }, coll);
+    clear_inner_layer<float>(1, bdry, vort1, cutoff, ips);
+    if (ref_derivs(fs, vort1, bdry, 1, time + 0.5*dt, solve, user, vs, ss)) return -2;
+    std::vector<Collection> vort2 = vort;
+    {
+      Points<float>& p1 = std::get<Points<float>>(vort1[0]);
+      Points<float>& p2 = std::get<Points<float>>(vort2[0]);
+      p2.move(time, 0.75*dt, 1.0, p1);
+    }
+    clear_inner_layer<float>(1, bdry, vort2, cutoff, ips);
+    if (ref_derivs(fs, vort2, bdry, 2, time + 0.75*dt, solve, user, vs, ss)) return -2;
+    Points<float>& p0 = std::get<Points<float>>(vort[0]);
+    Points<float>& p1 = std::get<Points<float>>(vort1[0]);
+    Points<float>& p2 = std::get<Points<float>>(vort2[0]);
+    p0.move(time, dt, 2.0/9.0, p0, 3.0/9.0, p1, 4.0/9.0, p2);
+    clear_inner_layer<float>(1, bdry, vort, cutoff, ips);
+  }
+  get_xu(vort[0], n, x, y, u, v);
+  return 0;
+}
+
+
 // ---- BEM coefficients -----------------------------------------------------------------------------
 // reference panels_on_panels_coeff<float> (src/Coefficients.h:155-573) called on the reference's
 // own Surfaces.  same != 0: one surface acting on itself (self-influence diagonal).  The reference
