@@ -6,6 +6,8 @@
 // -> finalize -- is restated here around the same InfluenceVisitor.
 #pragma once
 #include "InfluenceB200.h"
+#include <cmath>
+#include <type_traits>
 #include <variant>
 #include <vector>
 
@@ -83,6 +85,46 @@ void advect_particles(const int _order, const double _dt, const std::array<doubl
                                    u[0].data(), u[1].data(), 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
                                    _fs[0], _fs[1], _dt, _nsteps),
                   "advect_particles");
+}
+
+// One convection step of a flow with a body, all Runge-Kutta stages on the GPU (o2d_advect_bodies):
+// Convection::advect_1st / advect_2nd_ralston / advect_3rd (reference src/Convection.h:277-595) for one Lagrangian
+// Points collection and one Surfaces boundary, INCLUDING what the reference does between the stages: the right-hand
+// side of solve_bem (points_affect_panels + finalize_vels on the panels, src/BEMHelper.h:88-100), find_vels with the
+// newly solved strengths, Points::move and clear_inner_layer(1, ...).  The linear solve stays the application's:
+//   _solve(stage, time, pu, pv, vs, ss)   pu,pv: finalised particle-induced velocities at the panel centres
+//                                          (Surfaces::get_vel as vels_to_rhs_panels reads it); fills the new sheet
+//                                          strengths vs (and ss when the surface carries source strengths)
+// e.g. a lambda around vels_to_rhs_panels + BEM::set_rhs/solve/get_str.  The particles are uploaded once and
+// downloaded once per step; per stage 2*Np floats travel each way.  _surf's strength arrays end up holding the
+// strengths of the last stage, as after the reference's last solve_bem.
+template <class S, class SolveFn>
+void advect_with_body(const int _order, const double _time, const double _dt, const std::array<double,Dimensions>& _fs,
+                      const S _ips, Points<S>& _pts, Surfaces<S>& _surf, SolveFn&& _solve) {
+  struct Tramp {
+    static int call(void* user, int stage, double time, int np, const float* pu, const float* pv, float* vs, float* ss) {
+      try {
+        (*static_cast<std::remove_reference_t<SolveFn>*>(user))(stage, time, np, pu, pv, vs, ss);
+        return 0;
+      } catch (...) {
+        return 1;   // never let an exception cross the C boundary
+      }
+    }
+  };
+  static_assert(std::is_same<S, float>::value, "the B200 path stores float, like the reference (STORE=float)");
+  auto& x = _pts.get_pos();
+  auto& u = _pts.get_vel();
+  const auto& px = _surf.get_pos();
+  const auto& nrm = _surf.get_norm();
+  o2d_host::check(o2d_advect_bodies(o2d_host::device(), o2d_host::selected_core(), _order, O2D_MEM_HOST, (int)_pts.get_n(),
+                                    x[0].data(), x[1].data(), _pts.get_str().data(), _pts.get_rad().data(),
+                                    u[0].data(), u[1].data(), (int)_surf.get_npanels(), (int)_surf.get_n(),
+                                    px[0].data(), px[1].data(), _surf.get_idx().data(), _surf.get_area().data(),
+                                    nrm[0].data(), nrm[1].data(), _surf.get_str().data(),
+                                    _surf.have_src_str() ? _surf.get_src_str().data() : nullptr,
+                                    _fs[0], _fs[1], _time, _dt, (float)(0.5 / std::sqrt(2.0 * M_PI)), (float)_ips,
+                                    &Tramp::call, &_solve),
+                  "advect_with_body");
 }
 
 template <class S, class A>

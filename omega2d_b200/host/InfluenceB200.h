@@ -24,6 +24,8 @@
 #include <cassert>
 #include <chrono>
 #include <cstdio>
+#include <stdexcept>
+#include <string>
 #include <cstdlib>
 
 namespace o2d_host {
@@ -42,6 +44,13 @@ constexpr int selected_core() {
 #endif
 }
 
+// The reference's influence functions return void and assert; a library failure (no sm_100 GPU, CUDA error, bad
+// argument) is reported by an exception instead of taking the process down, so a GUI session can show it.  A host
+// program that does not catch it terminates with the message, as an assert would.
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
 // process-wide device group, created on first use: one GPU -- device $O2D_DEVICE, default 0 -- unless
 // $O2D_DEVICES=N|all asks for several; the reference is a single-process OpenMP program, so this is how it
 // reaches all GPUs of a box (include/omega2d_b200.h, "all GPUs of the box from ONE process")
@@ -57,10 +66,7 @@ inline o2d_group* group() {
       if (const char* e1 = std::getenv("O2D_DEVICE")) dev = std::atoi(e1);
       rc = o2d_group_create(&g, 1, &dev);
     }
-    if (rc != O2D_OK) {
-      std::fprintf(stderr, "omega2d_b200: %s\n", o2d_last_error());
-      std::abort();
-    }
+    if (rc != O2D_OK) throw Error(std::string("omega2d_b200: ") + o2d_last_error());   // no GPU: no CPU fallback either
     return g;
   }();
   return grp;
@@ -69,10 +75,7 @@ inline o2d_group* group() {
 inline o2d_context* device() { return o2d_group_context(group(), 0); }
 
 inline void check(int rc, const char* what) {
-  if (rc != O2D_OK) {
-    std::fprintf(stderr, "omega2d_b200: %s failed: %s\n", what, o2d_last_error());
-    std::abort();
-  }
+  if (rc != O2D_OK) throw Error(std::string("omega2d_b200: ") + what + " failed: " + o2d_last_error());
 }
 
 inline bool verbose() {

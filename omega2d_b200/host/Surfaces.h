@@ -3,6 +3,7 @@
 // influence path reads and writes: node positions, panel node indices, panel lengths
 // ("area"), vortex and source sheet strengths, panel-centre velocities.
 #pragma once
+#include <algorithm>
 #ifndef OMEGA2D_REFERENCE_HEADERS
 #include "Points.h"
 
@@ -97,18 +98,31 @@ public:
     }
   }
 
-  // collocation points offset along the panel normal (into the fluid: left of node0->node1),
-  // used by panels_affect_panels (reference src/Influence.h:783-784)
-  ElementPacket<float> represent_as_particles(const S _offset, const S /*_vdelta*/) const {
-    std::vector<float> px(2 * np);
+  // Particle version of the panels (reference src/Surfaces.h:830-873): per panel nshed = 1 + int(area/(1.2 ips)) points
+  // spread along the panel and pushed _offset along its stored normal, each carrying 1/nshed of the panel's
+  // circulation; _ips < 0 means "use the first panel's length" (what panels_affect_panels passes).  Same expressions,
+  // and therefore the same float/double promotions, as the reference.
+  ElementPacket<float> represent_as_particles(const S _offset, const S _ips) const {
+    std::vector<float> px, vals;
+    px.reserve(Dimensions * np);
+    vals.reserve(np);
+    const std::array<Vector<S>,Dimensions>& norm = b[1];
+    S thisips = _ips;
+    if (_ips < 0.0) thisips = area[0];
     for (size_t i = 0; i < np; ++i) {
-      const size_t id0 = idx[2*i], id1 = idx[2*i+1];
-      const S tx = (this->x[0][id1] - this->x[0][id0]) / area[i];
-      const S ty = (this->x[1][id1] - this->x[1][id0]) / area[i];
-      px[2*i]   = S(0.5) * (this->x[0][id0] + this->x[0][id1]) - _offset * ty;
-      px[2*i+1] = S(0.5) * (this->x[1][id0] + this->x[1][id1]) + _offset * tx;
+      const Int id0 = idx[2*i];
+      const Int id1 = idx[2*i+1];
+      float this_str = ps[0] ? (*ps[0])[i] : 0.0f;
+      this_str *= area[i];
+      const size_t nshed = 1 + std::max(0, (int)(area[i] / (1.2*thisips)));
+      for (size_t j = 0; j < nshed; ++j) {
+        const S wgt = (1+2*j) / (S)(2*nshed);
+        px.emplace_back(wgt*this->x[0][id1] + (1.0-wgt)*this->x[0][id0] + _offset * norm[0][i]);
+        px.emplace_back(wgt*this->x[1][id1] + (1.0-wgt)*this->x[1][id0] + _offset * norm[1][i]);
+        vals.emplace_back(this_str / (S)nshed);
+      }
     }
-    return ElementPacket<float>(px, std::vector<Int>(), std::vector<float>(np, 0.0f), np, 0);
+    return ElementPacket<float>(px, std::vector<Int>(), vals, vals.size(), 0);
   }
 
   void zero_vels() {

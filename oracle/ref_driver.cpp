@@ -433,6 +433,53 @@ int o2dref_advect_bodies(int order, int n, float* x, float* y, const float* s, c
 }
 
 
+// ---- the adapter routes (src/Influence.h:774-795, :810-869) ---------------------------------------------------------
+// reference panels_affect_panels<float,double>: collocation points 1e-4 off the target panels
+// (Surfaces::represent_as_particles) as temporary Points; their velocities are ADDED to the target's panel velocities.
+int o2dref_panels_affect_panels(int nsp, int nsn, const float* snx, const float* sny, const uint32_t* sidx,
+                                const float* svs, const float* sss,
+                                int ntp, int ntn, const float* tnx, const float* tny, const uint32_t* tidx,
+                                float* pu, float* pv) {
+  StdoutMute mute;
+  std::vector<float> z((size_t)ntp, 0.0f);
+  Surfaces<float> src = make_surfaces(nsp, nsn, snx, sny, sidx, svs, sss);
+  Surfaces<float> targ = make_surfaces(ntp, ntn, tnx, tny, tidx, z.data(), z.data());
+  auto& u = targ.get_vel();
+  for (int i = 0; i < ntp; ++i) { u[0][i] = pu[i]; u[1][i] = pv[i]; }
+  panels_affect_panels<float,double>(src, targ, ResultsType(velonly), ExecEnv(true, direct, cpu_x86));
+  for (int i = 0; i < ntp; ++i) { pu[i] = u[0][i]; pv[i] = u[1][i]; }
+  return 0;
+}
+
+// reference points_affect_bricks / panels_affect_bricks<float,double> on a Volumes collection of `ne` first-order quads
+// over `nn` nodes (bx,by; qidx = 4 node indices per quad): node velocities (and, for particles with velandvort, node
+// vorticities) are ADDED to the Volumes' arrays; returned through u,v,(w).
+int o2dref_affect_bricks(int from_panels, int results,
+                         int ns, const float* sx, const float* sy, const float* ss, const float* sr,
+                         int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx, const float* pvs, const float* pss,
+                         int ne, int nn, const float* bx, const float* by, const uint32_t* qidx,
+                         float* u, float* v, float* w) {
+  StdoutMute mute;
+  std::vector<float> px(2 * (size_t)nn), val((size_t)nn, 0.0f);
+  for (int i = 0; i < nn; ++i) { px[2*i] = bx[i]; px[2*i+1] = by[i]; }
+  std::vector<Int> qi(qidx, qidx + 4 * (size_t)ne);
+  Volumes<float> vol(ElementPacket<float>(px, qi, val, (size_t)ne, 2), inert, fixed, nullptr);
+  if (results == velandvort) (void)vol.get_vort();
+  const ExecEnv env(true, direct, cpu_x86);
+  if (from_panels) {
+    Surfaces<float> src = make_surfaces(np, nnodes, nx, ny, idx, pvs, pss);
+    panels_affect_bricks<float,double>(src, vol, ResultsType((results_t)results), env);
+  } else {
+    Points<float> src = make_points(ns, sx, sy, ss, sr);
+    points_affect_bricks<float,double>(src, vol, ResultsType((results_t)results), env);
+  }
+  const auto& vu = vol.get_vel();
+  for (int i = 0; i < nn; ++i) { u[i] = vu[0][i]; v[i] = vu[1][i]; }
+  if (w && results == velandvort) { const auto& vw = vol.get_vort(); for (int i = 0; i < nn; ++i) w[i] = vw[i]; }
+  return 0;
+}
+
+
 // ---- BEM coefficients -----------------------------------------------------------------------------
 // reference panels_on_panels_coeff<float> (src/Coefficients.h:155-573) called on the reference's
 // own Surfaces.  same != 0: one surface acting on itself (self-influence diagonal).  The reference

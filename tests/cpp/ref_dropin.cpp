@@ -42,7 +42,34 @@ int o2dref_panels_on_panels_coeff(int nsrc, int nsnodes, const float* snx, const
                                   float* tarea, float* sarea);
 int o2dref_clear_inner_layer(int method, int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
                              int n, float* x, float* y, float* s, const float* r, float cutoff_factor, float ips);
+int o2dref_panels_affect_panels(int nsp, int nsn, const float* snx, const float* sny, const uint32_t* sidx,
+                                const float* svs, const float* sss,
+                                int ntp, int ntn, const float* tnx, const float* tny, const uint32_t* tidx, float* pu, float* pv);
+int o2dref_affect_bricks(int from_panels, int results,
+                         int ns, const float* sx, const float* sy, const float* ss, const float* sr,
+                         int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx, const float* pvs, const float* pss,
+                         int ne, int nn, const float* bx, const float* by, const uint32_t* qidx, float* u, float* v, float* w);
+typedef int (*bem_solve_fn)(void* user, int stage, double time, int np, const float* pu, const float* pv, float* vs, float* ss);
+int o2dref_advect_bodies(int order, int n, float* x, float* y, const float* s, const float* r, float* u, float* v,
+                         int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx, float* vs, float* ss,
+                         double fsx, double fsy, double time, double dt, float ips, bem_solve_fn solve, void* user);
 }
+
+// stand-in for the application's BEM solve (Eigen is not in this image): sheet strengths that cancel the tangential and
+// normal velocity at the panel centres.  The same function serves the reference-side step and the GPU-side step.
+struct SyntheticBem {
+  std::vector<float> tx, ty, nx, ny;
+  void operator()(int, double, int np, const float* pu, const float* pv, float* vs, float* ss) const {
+    for (int i = 0; i < np; ++i) {
+      vs[i] = -(pu[i] * tx[i] + pv[i] * ty[i]);
+      if (ss) ss[i] = -(pu[i] * nx[i] + pv[i] * ny[i]);
+    }
+  }
+  static int c_call(void* user, int stage, double time, int np, const float* pu, const float* pv, float* vs, float* ss) {
+    (*static_cast<const SyntheticBem*>(user))(stage, time, np, pu, pv, vs, ss);
+    return 0;
+  }
+};
 
 static double rel_err(const std::vector<float>& gu, const std::vector<float>& gv,
                       const std::vector<float>& wu, const std::vector<float>& wv) {
@@ -143,6 +170,108 @@ int main() {
     std::printf("  clear_inner_layer moved %zu particles\n", moved);
     check("clear_inner_layer (push): max |dx| against the reference", d, 1e-5);
     if (moved < 10) ++bad;
+  }
+  // panels_affect_panels (src/Influence.h:774-795) through the visitor: the body acting on a second, smaller body; the
+  // collocation points come from the reference's own Surfaces::represent_as_particles on both sides
+  {
+    const size_t np2 = 60;
+    std::vector<float> n2x(np2), n2y(np2), p2(2 * np2), v2(2 * np2, 0.0f);
+    std::vector<Int> i2(2 * np2);
+    for (size_t i = 0; i < np2; ++i) {
+      const float th = -6.2831853f * (float)i / (float)np2;
+      n2x[i] = 0.9f + 0.2f * std::cos(th); n2y[i] = 0.3f + 0.2f * std::sin(th);
+      p2[2*i] = n2x[i]; p2[2*i+1] = n2y[i];
+      i2[2*i] = (Int)i; i2[2*i+1] = (Int)((i + 1) % np2);
+    }
+    Collection second = Surfaces<float>(ElementPacket<float>(p2, i2, v2, np2, 1), active, fixed, nullptr);
+    InfluenceVisitor<float,double> visitor = {ResultsType(velonly), ExecEnv(true, direct, cpu_x86)};
+    std::visit([](auto& e) { e.zero_vels(); }, second);
+    std::visit(visitor, bdry[0], second);
+    std::vector<float> wu(np2, 0.0f), wv(np2, 0.0f);
+    o2dref_panels_affect_panels((int)np, (int)np, nx.data(), ny.data(), idx.data(), pvs.data(), pss.data(),
+                                (int)np2, (int)np2, n2x.data(), n2y.data(), i2.data(), wu.data(), wv.data());
+    const auto& u2 = std::get<Surfaces<float>>(second).get_vel();
+    check("panels_affect_panels: body on a second body", rel_err(u2[0], u2[1], wu, wv), 1e-5);
+    // ... and the body on itself (collocation points 1e-4 above its own panels: the near-field pair)
+    Collection self = bdry[0];
+    std::visit([](auto& e) { e.zero_vels(); }, self);
+    std::visit(visitor, bdry[0], self);
+    std::vector<float> su(np, 0.0f), sv(np, 0.0f);
+    o2dref_panels_affect_panels((int)np, (int)np, nx.data(), ny.data(), idx.data(), pvs.data(), pss.data(),
+                                (int)np, (int)np, nx.data(), ny.data(), idx.data(), su.data(), sv.data());
+    const auto& us = std::get<Surfaces<float>>(self).get_vel();
+    check("panels_affect_panels: body on itself", rel_err(us[0], us[1], su, sv), 1e-5);
+  }
+  // points_affect_bricks / panels_affect_bricks (src/Influence.h:810-869): a Volumes collection of 12 x 8 quads
+  {
+    const int gx = 13, gy = 9, nn = gx * gy, ne = (gx - 1) * (gy - 1);
+    std::vector<float> bx(nn), by(nn), pb(2 * nn), vb(nn, 0.0f);
+    for (int j = 0; j < gy; ++j) for (int i = 0; i < gx; ++i) {
+      bx[j*gx+i] = 1.2f + 0.05f * i; by[j*gx+i] = -0.2f + 0.05f * j;
+      pb[2*(j*gx+i)] = bx[j*gx+i]; pb[2*(j*gx+i)+1] = by[j*gx+i];
+    }
+    std::vector<Int> qi;
+    for (int j = 0; j < gy - 1; ++j) for (int i = 0; i < gx - 1; ++i) {
+      qi.push_back((Int)(j*gx+i)); qi.push_back((Int)(j*gx+i+1)); qi.push_back((Int)((j+1)*gx+i+1)); qi.push_back((Int)((j+1)*gx+i));
+    }
+    InfluenceVisitor<float,double> visitor = {ResultsType(velandvort), ExecEnv(true, direct, cpu_x86)};
+    Collection vol = Volumes<float>(ElementPacket<float>(pb, qi, vb, (size_t)ne, 2), inert, fixed, nullptr);
+    (void)std::get<Volumes<float>>(vol).get_vort();
+    std::visit([](auto& e) { e.zero_vels(); }, vol);
+    std::visit(visitor, vort[0], vol);
+    std::vector<float> wu(nn), wv(nn), ww(nn), zero(nn, 0.0f);
+    o2dref_affect_bricks(0, velandvort, (int)nv, vx.data(), vy.data(), vs.data(), vr.data(), 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
+                         ne, nn, bx.data(), by.data(), qi.data(), wu.data(), wv.data(), ww.data());
+    {
+      const Volumes<float>& V = std::get<Volumes<float>>(vol);
+      check("points_affect_bricks: node velocities", rel_err(V.get_vel()[0], V.get_vel()[1], wu, wv), 1e-5);
+      check("points_affect_bricks: node vorticities", rel_err(V.get_vort(), zero, ww, zero), 1e-5);
+    }
+    InfluenceVisitor<float,double> vvel = {ResultsType(velonly), ExecEnv(true, direct, cpu_x86)};
+    std::visit([](auto& e) { e.zero_vels(); }, vol);
+    std::visit(vvel, bdry[0], vol);
+    o2dref_affect_bricks(1, velonly, 0, nullptr, nullptr, nullptr, nullptr, (int)np, (int)np, nx.data(), ny.data(), idx.data(), pvs.data(), pss.data(),
+                         ne, nn, bx.data(), by.data(), qi.data(), wu.data(), wv.data(), nullptr);
+    const Volumes<float>& V = std::get<Volumes<float>>(vol);
+    check("panels_affect_bricks: node velocities", rel_err(V.get_vel()[0], V.get_vel()[1], wu, wv), 1e-5);
+  }
+  // a whole convection step with the body: advect_with_body (GPU: BEM right-hand side, solve callback, find_vels, move,
+  // clear_inner_layer per stage, particles resident) against the reference-side step restated around the reference's
+  // own pieces (oracle/ref_driver.cpp), same stand-in BEM solve on both sides
+  {
+    SyntheticBem bemfn;
+    bemfn.tx.resize(np); bemfn.ty.resize(np); bemfn.nx.resize(np); bemfn.ny.resize(np);
+    {
+      const Surfaces<float>& sf = std::get<Surfaces<float>>(bdry[0]);
+      for (size_t i = 0; i < np; ++i) { bemfn.tx[i] = sf.get_tang()[0][i]; bemfn.ty[i] = sf.get_tang()[1][i]; bemfn.nx[i] = sf.get_norm()[0][i]; bemfn.ny[i] = sf.get_norm()[1][i]; }
+    }
+    const float ips = 0.02191f;
+    const double dt = 0.02;
+    for (int order = 1; order <= 3; ++order) {
+      // particles pulled towards the body so that the clear layer has work to do
+      std::vector<float> qx(nv), qy(nv), pq(2 * nv);
+      for (size_t i = 0; i < nv; ++i) { qx[i] = 0.92f * vx[i]; qy[i] = 0.92f * vy[i]; pq[2*i] = qx[i]; pq[2*i+1] = qy[i]; }
+      Points<float> pts(ElementPacket<float>(pq, std::vector<Int>(), vs, nv, 0), active, lagrangian, nullptr, vdelta);
+      Surfaces<float> surf = std::get<Surfaces<float>>(bdry[0]);
+      advect_with_body<float>(order, 0.0, dt, fs, ips, pts, surf, bemfn);
+      std::vector<float> wu(nv), wv(nv), ws(pvs), wss(pss);
+      o2dref_advect_bodies(order, (int)nv, qx.data(), qy.data(), vs.data(), vr.data(), wu.data(), wv.data(), (int)np, (int)np,
+                           nx.data(), ny.data(), idx.data(), ws.data(), wss.data(), fs[0], fs[1], 0.0, dt, ips, &SyntheticBem::c_call, &bemfn);
+      double d = 0.0; size_t flips = 0;
+      for (size_t i = 0; i < nv; ++i) {
+        const double di = std::hypot((double)pts.get_pos()[0][i] - qx[i], (double)pts.get_pos()[1][i] - qy[i]);
+        if (di > 2e-6) ++flips;     // the push threshold of clear_inner_layer is discontinuous
+        d = std::max(d, di);
+      }
+      char what[96];
+      std::snprintf(what, sizeof(what), "advect_with_body order %d: stage velocities", order);
+      check(what, rel_err(pts.get_vel()[0], pts.get_vel()[1], wu, wv), 1e-5);
+      std::snprintf(what, sizeof(what), "advect_with_body order %d: solved sheet strengths", order);
+      check(what, rel_err(surf.get_vort_str(), surf.get_src_str(), ws, wss), 1e-5);
+      std::snprintf(what, sizeof(what), "advect_with_body order %d: max |dx| (%zu threshold flips)", order, flips);
+      check(what, d, 0.0011 * ips + 2e-6);
+      if (flips > nv / 500) ++bad;
+    }
   }
   // BEM influence-coefficient block of the body on itself: CoefficientVisitor on the reference's Surfaces
   {

@@ -75,6 +75,12 @@ int main(int argc, char** argv) {
   dump(f, v.get_vel()[0]); dump(f, v.get_vel()[1]);
   dump(f, t.get_vel()[0]); dump(f, t.get_vel()[1]);
   dump(f, b.get_vel()[0]); dump(f, b.get_vel()[1]);
+  {   // the collocation points panels_affect_panels used for that (src/Influence.h:783)
+    const ElementPacket<float> cp = b.represent_as_particles(0.0001, -1.0);
+    std::vector<float> cx(cp.nelem), cy(cp.nelem);
+    for (size_t i = 0; i < cp.nelem; ++i) { cx[i] = cp.x[2*i]; cy[i] = cp.x[2*i+1]; }
+    dump(f, cx); dump(f, cy);
+  }
 
   // vel + vort on the particles (forced results type) and Gaussian vorticity on the tracers
   find_vels<float,double>(fs, vort, bdry, vort, velandvort, true);

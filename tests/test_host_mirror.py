@@ -43,7 +43,8 @@ def test_find_vels_cpp_vs_oracle(tmp_path, port):
     out = tmp_path / "fv.bin"
     subprocess.run([EXE, str(out), "3000", "143", "500"], check=True, env=dict(os.environ, USE_DEFAULT="1"))
     arrs = _read_arrays(out)
-    (vx, vy, vs_, vr, nx, ny, pvs, pss, area, fx, fy, vu, vv, fu, fv_, bu, bv, wu, wv, ww, fw) = arrs[:21]
+    (vx, vy, vs_, vr, nx, ny, pvs, pss, area, fx, fy, vu, vv, fu, fv_, bu, bv, cx, cy, wu, wv, ww, fw) = arrs[:23]
+    arrs = arrs[:21] + arrs[23:]   # the rest of the test indexes the dump without the two collocation arrays
     npan = pvs.size
     idx = np.empty(2 * npan, np.uint32); idx[0::2] = np.arange(npan); idx[1::2] = (np.arange(npan) + 1) % npan
     fs = (1.0, 0.0)
@@ -65,13 +66,13 @@ def test_find_vels_cpp_vs_oracle(tmp_path, port):
     # panel-centre velocities: reciprocity sum from the particles + panels on collocation points
     np.testing.assert_allclose(area, port.panel_areas(nx, ny, idx), rtol=1e-6)
     u, v = port.points_on_panels(vx, vy, vs_, nx, ny, idx, area)
+    # ... at the collocation points Surfaces::represent_as_particles produced (1e-4 off the sheet, one per panel here)
     i0, i1 = idx[0::2], idx[1::2]
-    tx_ = (nx[i1] - nx[i0]) / area; ty_ = (ny[i1] - ny[i0]) / area
-    cx = (0.5 * (nx[i0] + nx[i1]) - 1e-4 * ty_).astype(np.float32)
-    cy = (0.5 * (ny[i0] + ny[i1]) + 1e-4 * tx_).astype(np.float32)
+    assert cx.size == npan
+    np.testing.assert_allclose(cx, 0.5 * (nx[i0] + nx[i1]) - 1e-4 * (ny[i1] - ny[i0]) / area, atol=2e-7)
     pu, pv = port.panels_on_points(nx, ny, idx, pvs, pss, cx, cy)
     u, v, _, _ = finalize(u + pu, v + pv)
-    assert W.rel_err((bu, bv), (u, v)) < 5e-5   # collocation points sit 1e-4 off a singular sheet
+    assert W.rel_err((bu, bv), (u, v)) < tol
     # velocity + vorticity on the particles
     u, v, w = port.points_on_points("v2", oracle.VELANDVORT, vx, vy, vs_, vr, vx, vy, vr)
     u, v = port.panels_on_points(nx, ny, idx, pvs, pss, vx, vy, u, v)

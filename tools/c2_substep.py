@@ -21,7 +21,7 @@ import oracle
 from omega2d_b200 import workloads as W
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r01_c2_substep.md"))
+ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r02_c2_substep.md"))
 ap.add_argument("--sizes", default="10000,100000")
 args = ap.parse_args()
 
@@ -70,6 +70,19 @@ for n in [int(s) for s in args.sizes.split(",")]:
     cms, c = best(lambda: R.advect(2, x, y, s, r, 0.01, (nx, ny, idx, pvs, pss), fs), reps=1)
     rows.append((n, "advect, Ralston RK2 with the panel strengths held fixed (2 find_vels + moves)", 2.0 * n * (n + NP), gms, cms,
                  float(max(np.abs(g[0] - c[0]).max(), np.abs(g[1] - c[1]).max()))))
+
+    # the reference's whole RK2 step WITH the body: per stage BEM right-hand side -> solve -> find_vels -> move ->
+    # clear_inner_layer, particles resident on the GPU (o2d_advect_bodies); the linear solve is a stand-in callback
+    # (strengths cancelling the slip at the panel centres), identical on both sides and outside the path
+    def solve(stage, time_, pu, pv):
+        return (-(pu * ttx + pv * tty)).astype(np.float32), (-(pu * snx + pv * sny)).astype(np.float32)
+    z = np.zeros(NP, np.float32)
+    gms, g = best(lambda: ctx.advect_bodies_np("v2", 2, qx, qy, s, r, (nx, ny, idx, z, z), area, (snx, sny), solve, 0.01, IPS, fs))
+    cms, c = best(lambda: R.advect_bodies(2, qx, qy, s, r, (nx, ny, idx, z, z), solve, 0.01, IPS, fs), reps=1)
+    d = np.hypot(g[0] - c[0], g[1] - c[1])
+    rows.append((n, "advect_bodies, Ralston RK2 with the body: 2 x (BEM RHS, solve callback, find_vels, move, clear_inner_layer), "
+                    "ONE upload + ONE download of the particles" + (f" [{int((d > 2e-6).sum())} push-threshold flips]" if (d > 2e-6).any() else ""),
+                 2.0 * n * (n + 2 * NP), gms, cms, float(np.median(d)) if (d > 2e-6).any() else float(d.max())))
 
 info = ctx.device_info()
 with open(args.out, "w") as f:
