@@ -138,7 +138,7 @@ extern "C" int o2d_destroy(o2d_context* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   o2d_comm_destroy(c);
-  for (DevBuf* b : {&c->packed, &c->packed_all, &c->partial, &c->panel_packed, &c->hsrc, &c->htgt, &c->hout, &c->hidx, &c->hpan, &c->adv, &c->coef, &c->counter, &c->vtu})
+  for (DevBuf* b : {&c->packed, &c->packed_all, &c->partial, &c->panel_packed, &c->hsrc, &c->htgt, &c->hout, &c->hidx, &c->hpan, &c->adv, &c->coef, &c->counter, &c->vtu, &c->cil})
     b->release();
   if (c->vtu_host) cudaFreeHost(c->vtu_host);
   if (c->pin) cudaFreeHost(c->pin);
@@ -283,8 +283,8 @@ int o2d_pp_device(o2d_context* c, int core, int res,
 // costs ~10 us per call however small; an evaluation moves 10-15 arrays, which is most of the wall time of a
 // 10k-particle call (C1/C2 sizes).  Arrays up to kSmallCopy bytes therefore go through the context's pinned
 // buffer: memcpy + truly asynchronous DMA on the way in; DMA + memcpy after the final synchronise on the way out.
-static char* pin_take(o2d_context* c, size_t bytes) {
-  if (!c->pin || bytes > kSmallCopy) return nullptr;
+static char* pin_take(o2d_context* c, size_t bytes, size_t limit = kSmallCopy) {
+  if (!c->pin || bytes > limit) return nullptr;
   const size_t need = (bytes + 63) / 64 * 64;
   if (c->pin_off + need > c->pin_cap) return nullptr;
   char* p = c->pin + c->pin_off;
@@ -331,6 +331,51 @@ int o2d_finish_host(o2d_context* c) {
 }
 #define h2d o2d_h2d
 #define d2h o2d_d2h
+
+// span of a batch in device memory, if its items are ascending, non-overlapping and close together
+static bool batch_span(const std::vector<HostBatch::Item>& items, char** base, size_t* span) {
+  if (items.size() < 2) return false;
+  char* lo = static_cast<char*>(items.front().dev);
+  char* prev_end = lo;
+  for (const auto& it : items) {
+    char* d = static_cast<char*>(it.dev);
+    if (d < prev_end || (size_t)(d - prev_end) > 1024) return false;   // only padding between neighbours
+    prev_end = d + it.bytes;
+  }
+  *base = lo;
+  *span = (size_t)(prev_end - lo);
+  return true;
+}
+int HostBatch::upload() {
+  char* base; size_t span;
+  if (batch_span(items, &base, &span)) {
+    if (char* p = pin_take(c, span, 4 * kSmallCopy)) {
+      for (const auto& it : items) memcpy(p + (static_cast<char*>(it.dev) - base), it.host, it.bytes);
+      CU(cudaMemcpyAsync(base, p, span, cudaMemcpyHostToDevice, c->stream));
+      items.clear();
+      return O2D_OK;
+    }
+  }
+  for (const auto& it : items)
+    if (int rc = o2d_h2d_bytes(c, it.dev, it.host, it.bytes)) return rc;
+  items.clear();
+  return O2D_OK;
+}
+int HostBatch::download() {
+  char* base; size_t span;
+  if (batch_span(items, &base, &span)) {
+    if (char* p = pin_take(c, span, 4 * kSmallCopy)) {
+      CU(cudaMemcpyAsync(p, base, span, cudaMemcpyDeviceToHost, c->stream));
+      for (const auto& it : items) c->pending_out.push_back({it.host, p + (static_cast<char*>(it.dev) - base), it.bytes});
+      items.clear();
+      return O2D_OK;
+    }
+  }
+  for (const auto& it : items)
+    if (int rc = o2d_d2h_bytes(c, it.host, it.dev, it.bytes)) return rc;
+  items.clear();
+  return O2D_OK;
+}
 
 int o2d_check_common(o2d_context* c, int mem) {
   if (!c) return fail(O2D_ERR_INVALID, "ctx is NULL");
@@ -389,17 +434,18 @@ extern "C" int o2d_points_on_points(o2d_context* c, int core, int results, int m
   float *dsx = S.take(ns), *dsy = S.take(ns), *dss = S.take(ns), *dsr = S.take(ns);
   float *dtx = T.take(nt), *dty = T.take(nt), *dtr = tr ? T.take(nt) : nullptr;
   int rc;
-  if ((rc = h2d(c, dsx, sx, ns)) || (rc = h2d(c, dsy, sy, ns)) || (rc = h2d(c, dss, ss, ns)) ||
-      (rc = h2d(c, dsr, sr, ns)) || (rc = h2d(c, dtx, tx, nt)) || (rc = h2d(c, dty, ty, nt)))
-    return rc;
-  if (tr && (rc = h2d(c, dtr, tr, nt))) return rc;
+  HostBatch bs(c), bt(c), bo(c);
+  bs.add(dsx, sx, ns); bs.add(dsy, sy, ns); bs.add(dss, ss, ns); bs.add(dsr, sr, ns);
+  bt.add(dtx, tx, nt); bt.add(dty, ty, nt);
+  if (tr) bt.add(dtr, tr, nt);
   for (int k = 0; k < nout; ++k) {
     o.p[k] = O.take(nt);
-    if ((rc = h2d(c, o.p[k], outs[k], nt))) return rc;
+    bo.add(o.p[k], outs[k], nt);
   }
+  if ((rc = bs.upload()) || (rc = bt.upload()) || (rc = bo.upload())) return rc;
   if ((rc = o2d_pp_device(c, core, res, ns, dsx, dsy, dss, dsr, nt, dtx, dty, dtr, o))) return rc;
-  for (int k = 0; k < nout; ++k)
-    if ((rc = d2h(c, outs[k], o.p[k], nt))) return rc;
+  for (int k = 0; k < nout; ++k) bo.add(o.p[k], outs[k], nt);
+  if ((rc = bo.download())) return rc;
   if (int rc_ = o2d_finish_host(c)) return rc_;
   return O2D_OK;
 }

@@ -247,16 +247,17 @@ clear_inner_kernel(const CilArgs a) {
 
 }  // namespace
 
-int o2d_cil_device(o2d_context* c, int mode, int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
-                   const float* snx, const float* sny, int n, float* tx, float* ty, float cutoff_mult, float ips,
-                   unsigned long long* d_moved) {
+// panel-side preparation of a clear/reflect pass (node normals, packed panels, group bounds) into c->cil; the panels
+// of a body do not change between the Runge-Kutta stages of a step, so o2d_advect_bodies prepares once and runs per stage
+int o2d_cil_prepare(o2d_context* c, int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                    const float* snx, const float* sny) {
   // scratch: node normals (2*nnodes floats) + packed panels (3 float4 each) + group bounds (1 float4 per 32 panels)
   const size_t nn_bytes = ((2 * (size_t)nnodes * sizeof(float) + 255) / 256) * 256;
   const int ngroups = (np + kCilGroup - 1) / kCilGroup;
-  CU(c->panel_packed.reserve(nn_bytes + (size_t)np * 48 + (size_t)ngroups * 16));
-  float* nnx = c->panel_packed.as<float>();
+  CU(c->cil.reserve(nn_bytes + (size_t)np * 48 + (size_t)ngroups * 16));
+  float* nnx = c->cil.as<float>();
   float* nny = nnx + nnodes;
-  float4* packed = reinterpret_cast<float4*>(reinterpret_cast<char*>(c->panel_packed.p) + nn_bytes);
+  float4* packed = reinterpret_cast<float4*>(reinterpret_cast<char*>(c->cil.p) + nn_bytes);
   float4* bounds = packed + 3 * (size_t)np;
   CU(cudaMemsetAsync(nnx, 0, 2 * (size_t)nnodes * sizeof(float), c->stream));
   node_normals_kernel<<<(np + 255) / 256, 256, 0, c->stream>>>(np, idx, snx, sny, nnx, nny);
@@ -265,8 +266,20 @@ int o2d_cil_device(o2d_context* c, int mode, int np, int nnodes, const float* nx
   CU(cudaGetLastError());
   cil_group_bounds_kernel<<<(ngroups + 127) / 128, 128, 0, c->stream>>>(np, packed, bounds);
   CU(cudaGetLastError());
+  c->launches += 3;
+  c->cil_np = np;
+  c->cil_nn_bytes = nn_bytes;
+  return O2D_OK;
+}
+
+// the particle-side pass over the panels prepared last (mode 1 = clear_inner_layer push, 2 = reflect_interior)
+int o2d_cil_run(o2d_context* c, int mode, int n, float* tx, float* ty, float cutoff_mult, float ips,
+                unsigned long long* d_moved) {
+  const int np = c->cil_np;
+  float4* packed = reinterpret_cast<float4*>(reinterpret_cast<char*>(c->cil.p) + c->cil_nn_bytes);
   CilArgs a;
-  a.packed = packed; a.bounds = bounds; a.np = np; a.ngroups = ngroups; a.tx = tx; a.ty = ty; a.n = n;
+  a.packed = packed; a.bounds = packed + 3 * (size_t)np; a.np = np; a.ngroups = (np + kCilGroup - 1) / kCilGroup;
+  a.tx = tx; a.ty = ty; a.n = n;
   a.cutoff = cutoff_mult * ips; a.ips = ips; a.max_iter = 1000; a.moved = d_moved;
   {
     PairTimer timer(c);
@@ -276,9 +289,16 @@ int o2d_cil_device(o2d_context* c, int mode, int np, int nnodes, const float* nx
     else                   clear_inner_kernel<MODE_REFLECT><<<nb, kCilThreads, 0, c->stream>>>(a);
     CU(cudaGetLastError());
   }
-  c->launches += 4;
+  c->launches++;
   c->pair_launches++;
   return O2D_OK;
+}
+
+int o2d_cil_device(o2d_context* c, int mode, int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
+                   const float* snx, const float* sny, int n, float* tx, float* ty, float cutoff_mult, float ips,
+                   unsigned long long* d_moved) {
+  if (int rc = o2d_cil_prepare(c, np, nnodes, nx, ny, idx, snx, sny)) return rc;
+  return o2d_cil_run(c, mode, n, tx, ty, cutoff_mult, ips, d_moved);
 }
 
 static int cil_entry(o2d_context* c, int mode, int mem,

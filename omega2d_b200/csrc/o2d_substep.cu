@@ -129,9 +129,10 @@ int stage_panels(o2d_context* c, int np, int nnodes, const float* nx, const floa
   CU(c->hidx.reserve((size_t)2 * np * sizeof(uint32_t)));
   Stager S(c, &c->hpan);
   float *dnx = S.take(nnodes), *dny = S.take(nnodes), *dvs = S.take(np), *dss = ss ? S.take(np) : nullptr;
-  int rc;
-  if ((rc = o2d_h2d(c, dnx, nx, nnodes)) || (rc = o2d_h2d(c, dny, ny, nnodes)) || (rc = o2d_h2d(c, dvs, vs, np))) return rc;
-  if (ss && (rc = o2d_h2d(c, dss, ss, np))) return rc;
+  HostBatch bp(c);
+  bp.add(dnx, nx, nnodes); bp.add(dny, ny, nnodes); bp.add(dvs, vs, np);
+  if (ss) bp.add(dss, ss, np);
+  if (int rc_ = bp.upload()) return rc_;
   if (int rc_ = o2d_h2d_bytes(c, c->hidx.p, idx, (size_t)2 * np * sizeof(uint32_t))) return rc_;
   d->nx = dnx; d->ny = dny; d->idx = c->hidx.as<uint32_t>(); d->vs = dvs; d->ss = dss;
   return O2D_OK;
@@ -199,15 +200,17 @@ extern "C" int o2d_find_vels(o2d_context* c, int core, int results, int mem,
   float *dtx = T.take(nt), *dty = T.take(nt), *dtr = tr ? T.take(nt) : nullptr;
   float *dtu = O.take(nt), *dtv = O.take(nt), *dtq = tq ? O.take(nt) : nullptr;
   int rc;
-  if ((rc = o2d_h2d(c, dvx, vx, nv)) || (rc = o2d_h2d(c, dvy, vy, nv)) || (rc = o2d_h2d(c, dvs, vs, nv)) ||
-      (rc = o2d_h2d(c, dvr, vr, nv)) || (rc = o2d_h2d(c, dtx, tx, nt)) || (rc = o2d_h2d(c, dty, ty, nt)))
-    return rc;
-  if (tr && (rc = o2d_h2d(c, dtr, tr, nt))) return rc;
+  HostBatch bs(c), bt(c), bo(c);
+  bs.add(dvx, vx, nv); bs.add(dvy, vy, nv); bs.add(dvs, vs, nv); bs.add(dvr, vr, nv);
+  bt.add(dtx, tx, nt); bt.add(dty, ty, nt);
+  if (tr) bt.add(dtr, tr, nt);
+  if ((rc = bs.upload()) || (rc = bt.upload())) return rc;
   if ((rc = stage_panels(c, np, nnodes, nx, ny, idx, pvs, pss, &pan))) return rc;
   if ((rc = find_vels_device(c, core, res, nv, dvx, dvy, dvs, dvr, pan, nt, dtx, dty, dtr, dtu, dtv, dtq, fsx, fsy)))
     return rc;
-  if ((rc = o2d_d2h(c, tu, dtu, nt)) || (rc = o2d_d2h(c, tv, dtv, nt))) return rc;
-  if (res != RES_U && (rc = o2d_d2h(c, tq, dtq, nt))) return rc;
+  bo.add(dtu, tu, nt); bo.add(dtv, tv, nt);
+  if (res != RES_U) bo.add(dtq, tq, nt);
+  if ((rc = bo.download())) return rc;
   if (int rc_ = o2d_finish_host(c)) return rc_;
   return O2D_OK;
 }
@@ -385,14 +388,20 @@ int stage_derivs(o2d_context* c, int core, int n, const float* x, const float* y
   if ((rc = o2d_points_on_panels_device(c, n, x, y, s, np, b.pan.nx, b.pan.ny, b.pan.idx, b.area, b.pu, b.pv))) return rc;
   CU(launch_finalize(np, b.pu, b.pv, nullptr, nullptr, fsx, fsy, c->stream));
   c->launches++;
-  CU(cudaMemcpyAsync(h_pu, b.pu, (size_t)np * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaMemcpyAsync(h_pv, b.pv, (size_t)np * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  {
+    HostBatch down(c);
+    down.add(b.pu, h_pu, (size_t)np); down.add(b.pv, h_pv, (size_t)np);
+    if ((rc = down.download()) || (rc = o2d_finish_host(c))) return rc;   // waits for the stream: the stage's only host sync
+  }
   // the caller's BEM: RHS from these velocities, linear solve, new sheet strengths
   if (int urc = solve(user, stage, time, np, h_pu, h_pv, h_vs, h_ss))
     return fail(O2D_ERR_INVALID, "o2d_advect_bodies: the solve callback returned %d at stage %d", urc, stage);
-  CU(cudaMemcpyAsync(b.vs, h_vs, (size_t)np * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  if (b.ss) CU(cudaMemcpyAsync(b.ss, h_ss, (size_t)np * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  {
+    HostBatch up(c);
+    up.add(b.vs, h_vs, (size_t)np);
+    if (b.ss) up.add(b.ss, h_ss, (size_t)np);
+    if ((rc = up.upload())) return rc;
+  }
   // find_vels(fs, vort, bdry, vort)
   return find_vels_device(c, core, RES_U, n, x, y, s, r, b.pan, n, x, y, r, u, v, nullptr, fsx, fsy);
 }
@@ -432,37 +441,30 @@ extern "C" int o2d_advect_bodies(o2d_context* c, int core, int order, int mem,
   float *x1 = A.take(n), *y1 = A.take(n), *u1 = A.take(n), *v1 = A.take(n);
   float *x2 = A.take(n), *y2 = A.take(n), *u2 = A.take(n), *v2 = A.take(n);
   float *dnx = Pn.take(nnodes), *dny = Pn.take(nnodes);
+  float *darea = Pn.take(np), *dsnx = Pn.take(np), *dsny = Pn.take(np);
   BodyDev b;
   b.vs = Pn.take(np); b.ss = pss ? Pn.take(np) : nullptr;
-  float *darea = Pn.take(np), *dsnx = Pn.take(np), *dsny = Pn.take(np);
   b.pu = Pn.take(np); b.pv = Pn.take(np);
-  if ((rc = o2d_h2d(c, dx, x, n)) || (rc = o2d_h2d(c, dy, y, n)) || (rc = o2d_h2d(c, ds, s, n)) || (rc = o2d_h2d(c, dr, r, n)) ||
-      (rc = o2d_h2d(c, dnx, nx, nnodes)) || (rc = o2d_h2d(c, dny, ny, nnodes)) || (rc = o2d_h2d(c, darea, area, np)) ||
-      (rc = o2d_h2d(c, dsnx, snx, np)) || (rc = o2d_h2d(c, dsny, sny, np)))
-    return rc;
+  {
+    HostBatch bp(c), bb(c);
+    bp.add(dx, x, n); bp.add(dy, y, n); bp.add(ds, s, n); bp.add(dr, r, n);
+    bb.add(dnx, nx, nnodes); bb.add(dny, ny, nnodes); bb.add(darea, area, np); bb.add(dsnx, snx, np); bb.add(dsny, sny, np);
+    if ((rc = bp.upload()) || (rc = bb.upload())) return rc;
+  }
   if ((rc = o2d_h2d_bytes(c, c->hidx.p, idx, (size_t)2 * np * sizeof(uint32_t)))) return rc;
   b.pan.np = np; b.pan.nx = dnx; b.pan.ny = dny; b.pan.idx = c->hidx.as<uint32_t>(); b.pan.vs = b.vs; b.pan.ss = b.ss;
   b.area = darea; b.snx = dsnx; b.sny = dsny; b.nnodes = nnodes;
-  // host side of the per-stage exchange: 2*Np floats out, 2*Np back (pinned when the context has the room)
-  std::vector<float> hbuf;
-  float* h_pu; float* h_pv;
-  const size_t need = 2 * (size_t)np * sizeof(float);
-  if (c->pin && c->pin_off + need + 128 <= c->pin_cap) {
-    h_pu = reinterpret_cast<float*>(c->pin + ((c->pin_off + 63) / 64) * 64);
-    h_pv = h_pu + np;
-    c->pin_off = ((c->pin_off + 63) / 64) * 64 + need;
-  } else {
-    hbuf.resize(2 * (size_t)np);
-    h_pu = hbuf.data(); h_pv = h_pu + np;
-  }
+  // host side of the per-stage exchange: 2*Np floats out (one DMA), 2*Np back (one DMA)
+  std::vector<float> hbuf(2 * (size_t)np);
+  float* h_pu = hbuf.data();
+  float* h_pv = h_pu + np;
   const int nb = (n + 255) / 256;
   const float fdt = (float)dt;   // "(S)_dt" in ElementBase::move
   auto derivs = [&](int stage, double t, const float* px, const float* py, float* pu_, float* pv_) {
     return stage_derivs(c, core, n, px, py, ds, dr, pu_, pv_, b, h_pu, h_pv, pvs, pss, fsx, fsy, stage, t, solve, user);
   };
-  auto clear = [&](float* px, float* py) {
-    return o2d_cil_device(c, 1, np, nnodes, dnx, dny, b.pan.idx, dsnx, dsny, n, px, py, cutoff_mult, ips, nullptr);
-  };
+  if ((rc = o2d_cil_prepare(c, np, nnodes, dnx, dny, b.pan.idx, dsnx, dsny))) return rc;   // the body is fixed within the step
+  auto clear = [&](float* px, float* py) { return o2d_cil_run(c, 1, n, px, py, cutoff_mult, ips, nullptr); };
   if ((rc = derivs(0, time, dx, dy, du, dv))) return rc;
   if (order == 1) {
     // advect_1st (src/Convection.h:277-308)
@@ -498,8 +500,12 @@ extern "C" int o2d_advect_bodies(o2d_context* c, int core, int order, int mem,
     if ((rc = clear(dx, dy))) return rc;
   }
   // ---- one download -------------------------------------------------------------------------------------------------------
-  if ((rc = o2d_d2h(c, x, dx, n)) || (rc = o2d_d2h(c, y, dy, n)) || (rc = o2d_d2h(c, u, du, n)) || (rc = o2d_d2h(c, v, dv, n)))
-    return rc;
+  {
+    HostBatch bx(c), bu(c);
+    bx.add(dx, x, n); bx.add(dy, y, n);
+    bu.add(du, u, n); bu.add(dv, v, n);
+    if ((rc = bx.download()) || (rc = bu.download())) return rc;
+  }
   if (int rc_ = o2d_finish_host(c)) return rc_;
   return O2D_OK;
 }

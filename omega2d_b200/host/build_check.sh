@@ -15,6 +15,9 @@ echo "built build/test_find_vels"
 g++ -std=c++17 -O2 -Wall -I"$HERE" "$ROOT/examples/speedtest20kx10.cpp" \
     -L"$ROOT/omega2d_b200" -lomega2d_b200 -Wl,-rpath,'$ORIGIN/../omega2d_b200' -o "$ROOT/build/speedtest20kx10"
 echo "built build/speedtest20kx10"
+g++ -std=c++17 -O2 -Wall -I"$HERE" "$ROOT/examples/flow_over_circle_step.cpp" \
+    -L"$ROOT/omega2d_b200" -lomega2d_b200 -Wl,-rpath,'$ORIGIN/../omega2d_b200' -o "$ROOT/build/flow_over_circle_step"
+echo "built build/flow_over_circle_step"
 if [ -d "$REF/src" ]; then
   cat > "$ROOT/build/ref_containers_check.cpp" <<'CPP'
 // the reference's containers + this repository's influence header instead of Influence.h
