@@ -90,7 +90,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
-    ap.add_argument("--n", type=int, default=0, help="override the particle count at 1 GPU")
+    ap.add_argument("--n", "--particles", dest="n", type=int, default=0, help="override the particle count at 1 GPU")
     ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
                     help="default: the workload's own (weak, except c4: strong)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of one cpu_baseline sample")

@@ -162,6 +162,23 @@ int o2d_find_vels(o2d_context* ctx, int core, int results, int mem,
                   float* tu, float* tv, float* tq, double fsx, double fsy);
 
 /*
+ * Convection::find_vels for ANY number of source collections: the reference loops "for src in vort: visit;
+ * for src in bdry: visit" (src/Convection.h:205-213), i.e. one influence call per (source, target) pair.  Here every
+ * Points source is packed behind the previous one and summed by ONE pair-sum launch, every Surfaces source likewise by
+ * ONE panel launch, around one zero and one finalize: with host arrays that is one upload of all collections and one
+ * download of the target's results however many collections the simulation holds (particles of several bodies, Points
+ * boundaries, several Surfaces).  Otherwise as o2d_find_vels.
+ */
+typedef struct o2d_points_view { int n; const float* x; const float* y; const float* s; const float* r; } o2d_points_view;
+typedef struct o2d_panels_view {
+  int np; int nnodes; const float* nx; const float* ny; const uint32_t* idx; const float* vs; const float* ss;
+} o2d_panels_view;
+int o2d_find_vels_multi(o2d_context* ctx, int core, int results, int mem,
+                        int nsrc, const o2d_points_view* src, int npan, const o2d_panels_view* pan,
+                        int nt, const float* tx, const float* ty, const float* tr,
+                        float* tu, float* tv, float* tq, double fsx, double fsy);
+
+/*
  * One convection step of a Lagrangian particle collection, all stages on the GPU:
  * Convection::advect_1st (order 1, reference src/Convection.h:277-308), advect_2nd_ralston
  * (order 2, :314-392) or advect_3rd (order 3, :472-595) with ElementBase::move

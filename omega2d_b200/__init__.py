@@ -35,6 +35,15 @@ _up = C.POINTER(C.c_uint32)
 BEM_SOLVE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_int, _fp, _fp, _fp, _fp)
 
 
+class PointsView(C.Structure):      # o2d_points_view
+    _fields_ = [("n", C.c_int), ("x", C.c_void_p), ("y", C.c_void_p), ("s", C.c_void_p), ("r", C.c_void_p)]
+
+
+class PanelsView(C.Structure):      # o2d_panels_view
+    _fields_ = [("np", C.c_int), ("nnodes", C.c_int), ("nx", C.c_void_p), ("ny", C.c_void_p), ("idx", C.c_void_p),
+                ("vs", C.c_void_p), ("ss", C.c_void_p)]
+
+
 def bem_solve_callback(fn):
     """Wrap fn(stage, time, pu, pv) -> (vs, ss|None) (numpy float32 arrays) as an o2d_bem_solve_fn."""
     def trampoline(user, stage, time, npan, pu, pv, vs, ss):
@@ -100,6 +109,8 @@ def load_library() -> C.CDLL:
                                   i, vp, vp, vp, vp, vp, vp, d, d]
     lib.o2d_advect.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, d, d, d]
     lib.o2d_advect_steps.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, d, d, d, i]
+    lib.o2d_find_vels_multi.argtypes = [vp, i, i, i, i, C.POINTER(PointsView), i, C.POINTER(PanelsView),
+                                        i, vp, vp, vp, vp, vp, vp, d, d]
     lib.o2d_advect_bodies.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp,
                                       d, d, d, d, C.c_float, C.c_float, BEM_SOLVE_FN, vp]
     lib.o2d_panels_on_panels_coeff.argtypes = [vp, i, i, i, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp,
@@ -467,6 +478,32 @@ class Context:
         tq = np.empty(nt, np.float32) if results in (VELANDVORT, VELANDSHEAR) else None
         self.find_vels(core, results, MEM_HOST, 0 if vx is None else vx.size, vx, vy, vs, vr, npan, nn, nx, ny, idx,
                        pvs, pss, nt, tx, ty, tr, tu, tv, tq, fs)
+        return (tu, tv) if tq is None else (tu, tv, tq)
+
+    def find_vels_multi_np(self, core, results, vorts, panels, tx, ty, tr=None, fs=(0.0, 0.0)):
+        """vorts = list of (x, y, s, r); panels = list of (nx, ny, idx, vs, ss|None): o2d_find_vels_multi on host arrays."""
+        core = CORE_ID[core] if isinstance(core, str) else int(core)
+        tx, ty, tr = map(_f32, (tx, ty, tr))
+        nt = tx.size
+        keep = []
+        pv = (PointsView * max(len(vorts), 1))()
+        for k, vv in enumerate(vorts):
+            a = [_f32(q) for q in vv]
+            keep.append(a)
+            pv[k] = PointsView(a[0].size, *[q.ctypes.data for q in a])
+        qv = (PanelsView * max(len(panels), 1))()
+        for k, pp in enumerate(panels):
+            nx, ny, pvs = map(_f32, (pp[0], pp[1], pp[3]))
+            pss = None if pp[4] is None else _f32(pp[4])
+            idx = np.ascontiguousarray(pp[2], dtype=np.uint32)
+            keep.append((nx, ny, idx, pvs, pss))
+            qv[k] = PanelsView(pvs.size, nx.size, nx.ctypes.data, ny.ctypes.data, idx.ctypes.data, pvs.ctypes.data,
+                               None if pss is None else pss.ctypes.data)
+        tu, tv = np.empty(nt, np.float32), np.empty(nt, np.float32)
+        tq = np.empty(nt, np.float32) if results in (VELANDVORT, VELANDSHEAR) else None
+        self._check(self.lib.o2d_find_vels_multi(self._h, core, int(results), MEM_HOST, len(vorts), pv, len(panels), qv,
+                                                 nt, _ptr(tx), _ptr(ty), _ptr(tr), _ptr(tu), _ptr(tv), _ptr(tq),
+                                                 float(fs[0]), float(fs[1])))
         return (tu, tv) if tq is None else (tu, tv, tq)
 
     def advect_np(self, core, order, x, y, s, r, dt, panels=None, fs=(0.0, 0.0)):

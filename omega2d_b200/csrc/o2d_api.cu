@@ -278,6 +278,33 @@ int o2d_pp_device(o2d_context* c, int core, int res,
   return pp_run_packed(c, core, res, c->packed.as<float4>(), ns_padded, tx, ty, tr, nt, out);
 }
 
+int o2d_pp_multi_device(o2d_context* c, int core, int res, int nsrc, const o2d_points_view* src,
+                        int nt, const float* tx, const float* ty, const float* tr, const OutPtrs& out) {
+  long long total = 0;
+  int last = -1;
+  for (int k = 0; k < nsrc; ++k) if (src[k].n > 0) { total += ((long long)src[k].n + 1) / 2 * 2; last = k; }
+  if (last < 0 || nt <= 0) return O2D_OK;
+  const long long ns_padded = (total + kTile - 1) / kTile * kTile;
+  if (ns_padded > INT_MAX) return fail(O2D_ERR_INVALID, "more than 2^31 particles in one evaluation");
+  CU(c->packed.reserve((size_t)ns_padded * 16));
+  float4* packed = c->packed.as<float4>();
+  const int mode = res == RES_VORT ? 100 : core;
+  long long off = 0;
+  for (int k = 0; k < nsrc; ++k) {
+    if (src[k].n <= 0) continue;
+    const int even = (src[k].n + 1) / 2 * 2;
+    CU(launch_pack_sources(mode, src[k].n, src[k].x, src[k].y, src[k].s, src[k].r, packed + off, even, c->stream));
+    c->launches++;
+    off += even;
+  }
+  if (ns_padded > off) {   // tail of the last tile: zero-strength copies of the last collection's last particle
+    CU(launch_pack_sources(mode, src[last].n, src[last].x, src[last].y, src[last].s, src[last].r, packed + off,
+                           (int)(ns_padded - off), c->stream, src[last].n));
+    c->launches++;
+  }
+  return pp_run_packed(c, core, res, packed, ns_padded, tx, ty, tr, nt, out);
+}
+
 // ---- host staging helpers ----------------------------------------------------------------------------------
 // Host arrays are the caller's pageable std::vector storage.  A pageable cudaMemcpy is staged by the driver and
 // costs ~10 us per call however small; an evaluation moves 10-15 arrays, which is most of the wall time of a
@@ -481,15 +508,9 @@ extern "C" int o2d_points_vorticity(o2d_context* c, int mem,
 }
 
 // ---- panels ------------------------------------------------------------------------------------------------
-int o2d_panels_on_points_device(o2d_context* c, int np, const float* nx, const float* ny, const uint32_t* idx,
-                                   const float* vs, const float* ss, int nt, const float* tx, const float* ty,
-                                   float* tu, float* tv) {
-  if (np <= 0 || nt <= 0) return O2D_OK;
-  const int ntiles = (np + kPanelTile - 1) / kPanelTile;
-  const int np_padded = ntiles * kPanelTile;
-  CU(c->panel_packed.reserve((size_t)np_padded * 32));
-  CU(launch_pack_panels(np, nx, ny, idx, vs, ss, c->panel_packed.as<float4>(), np_padded, c->stream));
-  c->launches++;
+// panels already packed (np_padded of them, a multiple of kPanelTile) onto nt targets
+static int panels_run_packed(o2d_context* c, int np_padded, int nt, const float* tx, const float* ty, float* tu, float* tv) {
+  const int ntiles = np_padded / kPanelTile;
   // two targets per thread halve the shared-memory reads per pair; one per thread when that would leave SMs idle
   const int rpt = (nt >= 2 * 256 * c->sm_count * panels_occupancy(2) || (nt >= 256 * c->sm_count && ntiles >= 8)) ? 2 : 1;
   const int nb = (nt + 128 * rpt - 1) / (128 * rpt);
@@ -518,6 +539,43 @@ int o2d_panels_on_points_device(o2d_context* c, int np, const float* nx, const f
     c->launches++;
   }
   return O2D_OK;
+}
+
+int o2d_panels_multi_device(o2d_context* c, int npan, const o2d_panels_view* pan, int nt, const float* tx, const float* ty,
+                            float* tu, float* tv) {
+  long long total = 0;
+  int last = -1;
+  for (int k = 0; k < npan; ++k) if (pan[k].np > 0) { total += ((long long)pan[k].np + 1) / 2 * 2; last = k; }
+  if (last < 0 || nt <= 0) return O2D_OK;
+  const long long np_padded = (total + kPanelTile - 1) / kPanelTile * kPanelTile;
+  if (np_padded > INT_MAX) return fail(O2D_ERR_INVALID, "more than 2^31 panels in one evaluation");
+  CU(c->panel_packed.reserve((size_t)np_padded * 32));
+  float4* packed = c->panel_packed.as<float4>();   // 4 float4 per panel PAIR = 2 per panel
+  long long off = 0;
+  for (int k = 0; k < npan; ++k) {
+    if (pan[k].np <= 0) continue;
+    const int even = (pan[k].np + 1) / 2 * 2;
+    CU(launch_pack_panels(pan[k].np, pan[k].nx, pan[k].ny, pan[k].idx, pan[k].vs, pan[k].ss, packed + 2 * off, even, c->stream));
+    c->launches++;
+    off += even;
+  }
+  if (np_padded > off) {
+    CU(launch_pack_panels(pan[last].np, pan[last].nx, pan[last].ny, pan[last].idx, pan[last].vs, pan[last].ss, packed + 2 * off,
+                          (int)(np_padded - off), c->stream, pan[last].np));
+    c->launches++;
+  }
+  return panels_run_packed(c, (int)np_padded, nt, tx, ty, tu, tv);
+}
+
+int o2d_panels_on_points_device(o2d_context* c, int np, const float* nx, const float* ny, const uint32_t* idx,
+                                   const float* vs, const float* ss, int nt, const float* tx, const float* ty,
+                                   float* tu, float* tv) {
+  if (np <= 0 || nt <= 0) return O2D_OK;
+  const int np_padded = (np + kPanelTile - 1) / kPanelTile * kPanelTile;
+  CU(c->panel_packed.reserve((size_t)np_padded * 32));
+  CU(launch_pack_panels(np, nx, ny, idx, vs, ss, c->panel_packed.as<float4>(), np_padded, c->stream));
+  c->launches++;
+  return panels_run_packed(c, np_padded, nt, tx, ty, tu, tv);
 }
 
 extern "C" int o2d_panels_on_points(o2d_context* c, int mem,

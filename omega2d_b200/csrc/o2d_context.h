@@ -140,3 +140,8 @@ int o2d_cil_run(o2d_context* c, int mode, int n, float* tx, float* ty, float cut
 int o2d_cil_device(o2d_context* c, int mode, int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
                    const float* snx, const float* sny, int n, float* tx, float* ty, float cutoff_mult, float ips,
                    unsigned long long* d_moved);
+// several source collections behind one another: ONE pair-sum launch / ONE panel launch (o2d_find_vels_multi)
+int o2d_pp_multi_device(o2d_context* c, int core, int res, int nsrc, const o2d_points_view* src,
+                        int nt, const float* tx, const float* ty, const float* tr, const o2d::OutPtrs& out);
+int o2d_panels_multi_device(o2d_context* c, int npan, const o2d_panels_view* pan, int nt, const float* tx, const float* ty,
+                            float* tu, float* tv);

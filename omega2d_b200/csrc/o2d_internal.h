@@ -119,9 +119,10 @@ cudaError_t launch_pack_sources(int mode, int ns, const float* sx, const float* 
                                 const float* sr, float4* packed, int ns_padded, cudaStream_t st, int j0 = 0);
 
 // panels
+// writes np_padded (even) packed panels for panels j0, j0+1, ...: real ones below np, zero-strength copies of the last from np on
 cudaError_t launch_pack_panels(int np, const float* nx, const float* ny, const uint32_t* idx,
                                const float* vs, const float* ss, float4* packed, int np_padded,
-                               cudaStream_t st);
+                               cudaStream_t st, int j0 = 0);
 // rpt: targets per thread (1 or 2); grid.x covers 128*rpt targets per CTA
 cudaError_t launch_panels_on_points(const PanelArgs& a, int nchunks, int rpt, cudaStream_t st);
 cudaError_t launch_panels_combine(const double* partial, int nchunks, int nt, const OutPtrs& out, cudaStream_t st);

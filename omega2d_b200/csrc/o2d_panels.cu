@@ -33,7 +33,7 @@ namespace o2d {
 // (panel_far2 returns -ustar/2, -vstar/2), thr = |H|^2 / kFarZeta2: a target with |t - centre|^2 <= thr takes
 // the general panel_pair().
 __global__ void __launch_bounds__(256)
-pack_panels_kernel(int np, const float* __restrict__ nx, const float* __restrict__ ny,
+pack_panels_kernel(int np, int j0, const float* __restrict__ nx, const float* __restrict__ ny,
                    const uint32_t* __restrict__ idx, const float* __restrict__ vs,
                    const float* __restrict__ ss, float4* __restrict__ packed, int np_padded) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -41,7 +41,7 @@ pack_panels_kernel(int np, const float* __restrict__ nx, const float* __restrict
   float x0[2], y0[2], hx[2], hy[2], a[2], b[2], thr[2];
 #pragma unroll
   for (int l = 0; l < 2; ++l) {
-    const int j = 2 * q + l;
+    const int j = j0 + 2 * q + l;   // j >= np: padding = the last panel with zero strengths
     const int jj = j < np ? j : np - 1;
     const uint32_t i0 = idx[2 * jj], i1 = idx[2 * jj + 1];
     x0[l] = nx[i0]; y0[l] = ny[i0];
@@ -62,10 +62,10 @@ pack_panels_kernel(int np, const float* __restrict__ nx, const float* __restrict
 
 cudaError_t launch_pack_panels(int np, const float* nx, const float* ny, const uint32_t* idx,
                                const float* vs, const float* ss, float4* packed, int np_padded,
-                               cudaStream_t st) {
+                               cudaStream_t st, int j0) {
   if (np_padded <= 0) return cudaSuccess;
   const int nq = np_padded / 2;
-  pack_panels_kernel<<<(nq + 255) / 256, 256, 0, st>>>(np, nx, ny, idx, vs, ss, packed, np_padded);
+  pack_panels_kernel<<<(nq + 255) / 256, 256, 0, st>>>(np, j0, nx, ny, idx, vs, ss, packed, np_padded);
   return cudaGetLastError();
 }
 

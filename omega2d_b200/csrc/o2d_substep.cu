@@ -10,6 +10,7 @@
 // whole time step (o2d_advect): one upload, one download.
 #include "o2d_context.h"
 
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -258,6 +259,94 @@ extern "C" int o2d_find_vels_sharded(o2d_context* c, int core, int results, int 
     return rc;
   if ((rc = o2d_d2h(c, tu, dtu, nt)) || (rc = o2d_d2h(c, tv, dtv, nt))) return rc;
   if (res != RES_U && (rc = o2d_d2h(c, tq, dtq, nt))) return rc;
+  if (int rc_ = o2d_finish_host(c)) return rc_;
+  return O2D_OK;
+}
+
+extern "C" int o2d_find_vels_multi(o2d_context* c, int core, int results, int mem,
+                                   int nsrc, const o2d_points_view* src, int npan, const o2d_panels_view* pan,
+                                   int nt, const float* tx, const float* ty, const float* tr,
+                                   float* tu, float* tv, float* tq, double fsx, double fsy) {
+  if (int rc = o2d_check_common(c, mem)) return rc;
+  if (core < 0 || core > 4) return fail(O2D_ERR_INVALID, "unknown core %d", core);
+  if (results == O2D_PSIONLY || results == O2D_VELANDGRAD)
+    return fail(O2D_ERR_UNSUPPORTED, "find_vels computes vel, vel+vort or vel+shear (reference src/Convection.h:172-223)");
+  const int res = o2d_res_from_results(results);
+  if (res < 0) return fail(O2D_ERR_INVALID, "unknown results type %d", results);
+  if (nsrc < 0 || npan < 0 || nt < 0) return fail(O2D_ERR_INVALID, "negative count");
+  if ((nsrc > 0 && !src) || (npan > 0 && !pan)) return fail(O2D_ERR_INVALID, "NULL collection list");
+  for (int k = 0; k < nsrc; ++k) {
+    if (src[k].n < 0) return fail(O2D_ERR_INVALID, "negative count");
+    if (src[k].n > 0 && (!src[k].x || !src[k].y || !src[k].s || !src[k].r)) return fail(O2D_ERR_INVALID, "NULL particle array");
+  }
+  for (int k = 0; k < npan; ++k)
+    if (int rc = check_panels(pan[k].np, pan[k].nnodes, pan[k].nx, pan[k].ny, pan[k].idx, pan[k].vs)) return rc;
+  if (nt == 0) return O2D_OK;
+  if (!tx || !ty || !tu || !tv) return fail(O2D_ERR_INVALID, "NULL target array");
+  if (res != RES_U && !tq) return fail(O2D_ERR_INVALID, "tq must not be NULL for vorticity/shear results");
+  float* w = res == RES_UW ? tq : nullptr;
+  float* e = res == RES_UE ? tq : nullptr;
+  auto run = [&](const o2d_points_view* ds, const o2d_panels_view* dp, const float* dtx, const float* dty, const float* dtr,
+                 float* dtu, float* dtv, float* dtq) -> int {
+    CU(launch_zero(nt, dtu, dtv, res == RES_UW ? dtq : nullptr, res == RES_UE ? dtq : nullptr, c->stream));
+    c->launches++;
+    OutPtrs o{};
+    o.p[0] = dtu; o.p[1] = dtv; o.p[2] = dtq;
+    if (int rc = o2d_pp_multi_device(c, core, res, nsrc, ds, nt, dtx, dty, dtr, o)) return rc;
+    if (int rc = o2d_panels_multi_device(c, npan, dp, nt, dtx, dty, dtu, dtv)) return rc;
+    CU(launch_finalize(nt, dtu, dtv, res == RES_UW ? dtq : nullptr, res == RES_UE ? dtq : nullptr, fsx, fsy, c->stream));
+    c->launches++;
+    return O2D_OK;
+  };
+  (void)w; (void)e;
+  if (mem == O2D_MEM_DEVICE) return run(src, pan, tx, ty, tr, tu, tv, tq);
+  // host arrays: every collection goes up once, the target's results come down once
+  size_t sbytes = 256, pbytes = 256, ibytes = 256;
+  for (int k = 0; k < nsrc; ++k) sbytes += 4 * padded_floats(std::max(src[k].n, 0));
+  for (int k = 0; k < npan; ++k) {
+    for (int q = 0; q < 2 * pan[k].np; ++q)
+      if (pan[k].idx[q] >= (uint32_t)pan[k].nnodes) return fail(O2D_ERR_INVALID, "panel node index %u out of range", pan[k].idx[q]);
+    pbytes += 2 * padded_floats(pan[k].nnodes) + 2 * padded_floats(pan[k].np);
+    ibytes += ((size_t)2 * pan[k].np * sizeof(uint32_t) + 255) / 256 * 256;
+  }
+  CU(c->hsrc.reserve(sbytes));
+  CU(c->hpan.reserve(pbytes));
+  CU(c->hidx.reserve(ibytes));
+  CU(c->htgt.reserve(3 * padded_floats(nt)));
+  CU(c->hout.reserve(kMaxOut * padded_floats(nt)));
+  Stager S(c, &c->hsrc), Pn(c, &c->hpan), I(c, &c->hidx), T(c, &c->htgt), O(c, &c->hout);
+  std::vector<o2d_points_view> ds((size_t)nsrc);
+  std::vector<o2d_panels_view> dp((size_t)npan);
+  int rc;
+  HostBatch bs(c), bp(c), bi(c), bt(c), bo(c);
+  for (int k = 0; k < nsrc; ++k) {
+    const int n = src[k].n;
+    ds[k].n = n;
+    if (n <= 0) continue;
+    float *dx = S.take(n), *dy = S.take(n), *dss = S.take(n), *dr = S.take(n);
+    bs.add(dx, src[k].x, n); bs.add(dy, src[k].y, n); bs.add(dss, src[k].s, n); bs.add(dr, src[k].r, n);
+    ds[k].x = dx; ds[k].y = dy; ds[k].s = dss; ds[k].r = dr;
+  }
+  for (int k = 0; k < npan; ++k) {
+    const int np = pan[k].np, nn = pan[k].nnodes;
+    dp[k] = o2d_panels_view{np, nn, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (np <= 0) continue;
+    float *dnx = Pn.take(nn), *dny = Pn.take(nn), *dvs = Pn.take(np), *dss = pan[k].ss ? Pn.take(np) : nullptr;
+    uint32_t* di = reinterpret_cast<uint32_t*>(I.take((size_t)2 * np));
+    bp.add(dnx, pan[k].nx, nn); bp.add(dny, pan[k].ny, nn); bp.add(dvs, pan[k].vs, np);
+    if (dss) bp.add(dss, pan[k].ss, np);
+    bi.add((void*)di, (const void*)pan[k].idx, (size_t)2 * np * sizeof(uint32_t));
+    dp[k].nx = dnx; dp[k].ny = dny; dp[k].idx = di; dp[k].vs = dvs; dp[k].ss = dss;
+  }
+  float *dtx = T.take(nt), *dty = T.take(nt), *dtr = tr ? T.take(nt) : nullptr;
+  float *dtu = O.take(nt), *dtv = O.take(nt), *dtq = tq ? O.take(nt) : nullptr;
+  bt.add(dtx, tx, nt); bt.add(dty, ty, nt);
+  if (tr) bt.add(dtr, tr, nt);
+  if ((rc = bs.upload()) || (rc = bp.upload()) || (rc = bi.upload()) || (rc = bt.upload())) return rc;
+  if ((rc = run(ds.data(), dp.data(), dtx, dty, dtr, dtu, dtv, dtq))) return rc;
+  bo.add(dtu, tu, nt); bo.add(dtv, tv, nt);
+  if (res != RES_U) bo.add(dtq, tq, nt);
+  if ((rc = bo.download())) return rc;
   if (int rc_ = o2d_finish_host(c)) return rc_;
   return O2D_OK;
 }

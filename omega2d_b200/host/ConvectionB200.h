@@ -12,20 +12,36 @@
 #include <vector>
 
 namespace o2d_host {
-// One particle collection (+ at most one surface collection) acting on a Points target: the whole
-// zero -> accumulate -> finalize sequence is ONE library call (o2d_find_vels: one upload, one
-// download) instead of one call -- and one host<->device round trip -- per source collection.
+// All Points and Surfaces sources acting on a Points target: the whole zero -> accumulate -> finalize sequence is ONE
+// library call -- one upload of every collection, one pair-sum launch over all the particles, one panel launch over all
+// the panels, one download -- instead of one call, and one host<->device round trip, per (source, target) pair
+// (reference loop: src/Convection.h:205-213).  With one GPU per process this is o2d_find_vels_multi; with a device
+// group (O2D_DEVICES) and a single particle + surface collection it is o2d_group_find_vels.
 template <class S>
 bool fused_find_vels(const std::array<double,Dimensions>& _fs, std::vector<Collection>& _vort,
                      std::vector<Collection>& _bdry, Collection& _targ, const results_t _results) {
   if (_results != velonly && _results != velandvort && _results != velandshear) return false;
-  if (_vort.size() != 1 || !std::holds_alternative<Points<S>>(_vort[0])) return false;
-  if (_bdry.size() > 1 || (_bdry.size() == 1 && !std::holds_alternative<Surfaces<S>>(_bdry[0]))) return false;
   if (!std::holds_alternative<Points<S>>(_targ)) return false;
-  const Points<S>& src = std::get<Points<S>>(_vort[0]);
+  std::vector<o2d_points_view> pts;
+  std::vector<o2d_panels_view> pans;
+  for (auto* list : {&_vort, &_bdry})
+    for (auto& src : *list) {
+      if (std::holds_alternative<Points<S>>(src)) {
+        const Points<S>& p = std::get<Points<S>>(src);
+        if (p.is_inert()) return false;                               // no strengths to sum: the reference asserts in get_str()
+        pts.push_back(o2d_points_view{(int)p.get_n(), p.get_pos()[0].data(), p.get_pos()[1].data(), p.get_str().data(),
+                                      p.get_rad().data()});
+      } else if (std::holds_alternative<Surfaces<S>>(src)) {
+        const Surfaces<S>& q = std::get<Surfaces<S>>(src);
+        if (q.is_inert()) return false;
+        pans.push_back(o2d_panels_view{(int)q.get_npanels(), (int)q.get_n(), q.get_pos()[0].data(), q.get_pos()[1].data(),
+                                       q.get_idx().data(), q.get_str().data(),
+                                       q.have_src_str() ? q.get_src_str().data() : nullptr});
+      } else {
+        return false;                                                 // Volumes as a source: leave it to the visitor
+      }
+    }
   Points<S>& targ = std::get<Points<S>>(_targ);
-  const Surfaces<S>* pan = _bdry.empty() ? nullptr : &std::get<Surfaces<S>>(_bdry[0]);
-  const auto& sx = src.get_pos();
   const auto& tx = targ.get_pos();
   auto& tu = targ.get_vel();
   S* tq = nullptr;
@@ -34,14 +50,19 @@ bool fused_find_vels(const std::array<double,Dimensions>& _fs, std::vector<Colle
   // finalize_vels also scales whichever of w/e the collection carries; keep the one not computed here
   // consistent with the unfused sequence (zeroed, then scaled: stays zero)
   targ.zero_vels();
-  check(o2d_group_find_vels(group(), selected_core(), (int)_results,
-                      (int)src.get_n(), sx[0].data(), sx[1].data(), src.get_str().data(), src.get_rad().data(),
-                      pan ? (int)pan->get_npanels() : 0, pan ? (int)pan->get_n() : 0,
-                      pan ? pan->get_pos()[0].data() : nullptr, pan ? pan->get_pos()[1].data() : nullptr,
-                      pan ? pan->get_idx().data() : nullptr, pan ? pan->get_str().data() : nullptr,
-                      (pan && pan->have_src_str()) ? pan->get_src_str().data() : nullptr,
-                      (int)targ.get_n(), tx[0].data(), tx[1].data(), targ.is_inert() ? nullptr : targ.get_rad().data(),
-                      tu[0].data(), tu[1].data(), tq, _fs[0], _fs[1]),
+  const S* tr = targ.is_inert() ? nullptr : targ.get_rad().data();
+  if (o2d_group_size(group()) > 1 && pts.size() == 1 && pans.size() <= 1) {
+    const o2d_panels_view* q = pans.empty() ? nullptr : &pans[0];
+    check(o2d_group_find_vels(group(), selected_core(), (int)_results, pts[0].n, pts[0].x, pts[0].y, pts[0].s, pts[0].r,
+                              q ? q->np : 0, q ? q->nnodes : 0, q ? q->nx : nullptr, q ? q->ny : nullptr, q ? q->idx : nullptr,
+                              q ? q->vs : nullptr, q ? q->ss : nullptr,
+                              (int)targ.get_n(), tx[0].data(), tx[1].data(), tr, tu[0].data(), tu[1].data(), tq, _fs[0], _fs[1]),
+          "find_vels");
+    return true;
+  }
+  check(o2d_find_vels_multi(device(), selected_core(), (int)_results, O2D_MEM_HOST, (int)pts.size(), pts.data(),
+                            (int)pans.size(), pans.data(), (int)targ.get_n(), tx[0].data(), tx[1].data(), tr,
+                            tu[0].data(), tu[1].data(), tq, _fs[0], _fs[1]),
         "find_vels");
   return true;
 }

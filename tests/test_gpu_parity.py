@@ -448,3 +448,64 @@ def test_callable_from_a_non_main_thread_with_changing_sizes(ctx, port):
     assert "error" not in results, results.get("error")
     for n, (got, want) in results.items():
         assert W.rel_err(got, want[:2]) < 1e-5, n
+
+
+def test_find_vels_multi_collections(ctx, port):
+    """o2d_find_vels_multi: three particle collections (odd counts, one empty) and two surface collections on blob targets
+    and on inert targets -- ONE call, against the reference's loop order (zero; every source in turn; finalize) done
+    with the oracle; and with a single collection it is o2d_find_vels bit for bit."""
+    fs = (0.7, -0.2)
+    vorts = [W.gaussian_blob(n, seed=40 + n, signed=True) for n in (1501, 0, 2333)] + [W.annulus_blobs(777, seed=3)]
+    vorts = [tuple(np.asarray(a, np.float32) for a in v) for v in vorts]
+    pans = [W.circle_panels(143, radius=0.5, seed=1), W.circle_panels(61, radius=0.2, center=(1.1, 0.3), seed=2)]
+    pans = [(p[0], p[1], p[2], p[3], p[4]) for p in pans]
+    pans[1] = pans[1][:4] + (None,)                       # vortex-only second surface
+    for blob in (True, False):
+        tx, ty, _, tr = W.gaussian_blob(1999, seed=77, sigma=0.6)
+        tr = tr if blob else None
+        for results in (o2d.VELONLY, o2d.VELANDVORT):
+            got = ctx.find_vels_multi_np("v2", results, vorts, pans, tx, ty, tr, fs)
+            u = np.zeros(tx.size, np.float32); v = np.zeros(tx.size, np.float32); w = np.zeros(tx.size, np.float32)
+            for vx, vy, vs, vr in vorts:
+                if vx.size == 0:
+                    continue
+                r = port.points_on_points("v2", results, vx, vy, vs, vr, tx, ty, tr)
+                u += r[0]; v += r[1]
+                if results == o2d.VELANDVORT:
+                    w += r[2]
+            for nx, ny, idx, pvs, pss in pans:
+                pu, pv = port.panels_on_points(nx, ny, idx, pvs, pss, tx, ty)
+                u += pu; v += pv
+            want = port.finalize_vels(u, v, w if results == o2d.VELANDVORT else None, None, fs)
+            assert W.rel_err(got[:2], want[:2]) < TOL
+            if results == o2d.VELANDVORT:
+                assert W.rel_err(got[2], want[2]) < TOL
+    one = ctx.find_vels_multi_np("rm", o2d.VELONLY, [vorts[0]], [pans[0]], tx, ty, None, fs)
+    ref = ctx.find_vels_np("rm", o2d.VELONLY, vorts[0], pans[0], tx, ty, None, fs)
+    np.testing.assert_array_equal(one[0], ref[0]); np.testing.assert_array_equal(one[1], ref[1])
+    # no sources at all: the freestream
+    none = ctx.find_vels_multi_np("rm", o2d.VELONLY, [], [], tx, ty, None, fs)
+    np.testing.assert_array_equal(none[0], np.full(tx.size, np.float32(fs[0])))
+
+
+def test_sharded_entry_with_empty_block_and_exp_gradients(ctx, port):
+    """A rank that owns no particles packs a filler block (zero strength, far away, small radius): it must add exactly
+    nothing -- also for the EXP core's gradient results, whose pair term is NaN at zero distance, and also
+    for a target at the origin."""
+    sx, sy, ss, sr = W.gaussian_blob(3001, seed=8, signed=True)
+    tx = np.concatenate([[0.0], sx[:500] + 0.013]).astype(np.float32)
+    ty = np.concatenate([[0.0], sy[:500] - 0.007]).astype(np.float32)
+    tr = np.concatenate([[sr[0]], sr[:500]]).astype(np.float32)
+    for core in ("exp", "v3", "rm"):
+        outs = [np.zeros(tx.size, np.float32) for _ in range(3)]
+        ctx.points_on_points_sharded(core, o2d.VELANDVORT, o2d.MEM_HOST, 0, 4096, None, None, None, None,
+                                     tx.size, tx, ty, tr, outs[0], outs[1], outs[2])
+        for o in outs:
+            np.testing.assert_array_equal(o, np.zeros_like(o))
+        # one rank, block larger than the particle count: in-block padding + tile tail, same result as the plain call
+        got = [np.zeros(tx.size, np.float32) for _ in range(3)]
+        ctx.points_on_points_sharded(core, o2d.VELANDVORT, o2d.MEM_HOST, sx.size, 5000, sx, sy, ss, sr,
+                                     tx.size, tx, ty, tr, got[0], got[1], got[2])
+        want = ctx.points_on_points_np(core, o2d.VELANDVORT, sx, sy, ss, sr, tx, ty, tr)
+        for a, b in zip(got, want):
+            assert W.rel_err(a, b) < 1e-6
