@@ -99,6 +99,7 @@ def parse_args():
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="skip the fixed-size C4 block of the default (c3) run")
     ap.add_argument("--strong-steps", type=int, default=2)
+    ap.add_argument("--strong-particles", type=int, default=0, help="particle count of the C4 block (default: C4's 4 194 304; tests shrink it)")
     return ap.parse_args()
 
 
@@ -287,7 +288,7 @@ def strong_block(args, ctx, dev, stream, flush, world, rank, barrier):
     import torch.distributed as dist
     import omega2d_b200 as o2d
     wl = WORKLOADS["c4"]
-    n = wl["n"]
+    n = args.strong_particles or wl["n"]
     lo, hi = sharding.block_range(n, world, rank)
     nblock = sharding.block_size(n, world)
     nloc = hi - lo
@@ -587,9 +588,22 @@ def run_ours(args, wl, n1):
     ffma = ctx.measure_fp32_peak(False)
     ffma2 = ctx.measure_fp32_peak(True)
     traffic = ncu_traffic(core, results, n) if world == 1 else None
+    # hardware view: FP32 lane-ops per pair COUNTED by ncu on this kernel (FMA-pipe warp instructions x 64 lanes, capture at
+    # 1M x 1M in profiles/) x the pairs of this launch / the live kernel time, against what the FMA pipe retires
+    # (128 lane-ops per clock per SM); the XU (MUFU) pipe likewise against 16 per clock per SM
+    cap = ncu_traffic(core, results, 1_000_000)
+    hw = None
+    if cap and cap.get("fp32_lane_ops_per_launch") and kern_s > 0:
+        clk = info["sm_clock_mhz"] * 1e6 * info["sm_count"]
+        lane_pp, mufu_pp = cap["fp32_lane_ops_per_launch"] / 1e12, cap["mufu_lane_ops_per_launch"] / 1e12
+        hw = {"frac_hw": lane_pp * pairs_rank0 / kern_s / (128.0 * clk), "xu_frac_hw": mufu_pp * pairs_rank0 / kern_s / (16.0 * clk),
+              "fp32_lane_ops_per_pair": lane_pp, "mufu_per_pair": mufu_pp,
+              "fma_pipe_cycles_active_pct_under_ncu": cap["fma_pipe_cycles_active_pct"], "xu_pipe_pct_under_ncu": cap["xu_pipe_pct"],
+              "issue_active_pct_under_ncu": cap["issue_active_pct"], "source": cap["source"]}
     roofline = {
         "bound": "fp32", "achieved": achieved, "peak": peak_nominal, "unit": "TFLOP/s",
         "frac": achieved / peak_nominal if peak_nominal else None,
+        "frac_hw": hw["frac_hw"] if hw else None, "hardware": hw,
         "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
         "algorithmic_bytes_per_launch": 16 * n + 12 * nloc + 4 * nout * nloc,
         "flops_per_pair": flops_pp, "kernel": f"pp_kernel<{core},res{results}>",
@@ -598,7 +612,9 @@ def run_ours(args, wl, n1):
                        "(MEASURED_PEAKS.json has no FP32 non-tensor entry; its hbm/bf16 peaks do not bound this kernel)",
         "measured_ffma_tflops": ffma, "measured_ffma2_tflops": ffma2,
         "frac_of_measured_ffma2": achieved / ffma2 if ffma2 else None,
-        "note": "flops are the reference's own per-pair counters (src/Kernels.h, src/CoreFunc.h), not hardware ops",
+        "note": "`frac` counts the reference's own per-pair flops (src/Kernels.h, src/CoreFunc.h: 34 for velocity+gradient, where the "
+                "kernel executes 15 FP32 lane-ops + 1 MUFU), so it is an algorithmic rate, not hardware utilisation; `frac_hw` is the "
+                "FMA-pipe utilisation from ncu-counted instructions",
     }
 
     # ---- other kernels of the path on the same particle count (device-resident, kernel-only view) -----------

@@ -38,19 +38,19 @@ def _worker(rank, world, port_no, n, ret):
     sx, sy, ss, sr = W.onbody_random(n, seed=77)
     lo, hi = sharding.block_range(n, world, rank)
     nb = sharding.block_size(n, world)
-    # each rank packs its block into a buffer of the common capacity nb (padding = zero strength
-    # copies of its last particle, like pack_sources_kernel), then all ranks gather
-    mine = np.zeros((4, nb), np.float32)
+    # the layout of o2d_pp_sharded_device: every rank packs its block into its slot of `blk` entries (padding as
+    # pack_sources_kernel writes it), one all-gather replicates the slots, and each rank pads the tail of the last
+    # tile itself -- then ONE sum over the whole gathered array
+    blk, total = sharding.gather_layout(nb, world)
+    assert blk % 2 == 0 and blk >= nb and total % 1024 == 0 and total >= blk * world
     k = hi - lo
-    for row, a in enumerate((sx, sy, ss, sr)):
-        mine[row, :k] = a[lo:hi]
-        if k:
-            mine[row, k:] = a[hi - 1] if row != 2 else 0.0
-        elif row == 3:
-            mine[row, :] = 1.0
-    gathered = [torch.zeros(4, nb) for _ in range(world)]
+    local = [a[lo:hi] for a in (sx, sy, ss, sr)]
+    mine = np.stack(sharding.pad_block(local, blk))
+    gathered = [torch.zeros(4, blk) for _ in range(world)]
     dist.all_gather(gathered, torch.from_numpy(mine))
-    allsrc = torch.cat(gathered, dim=1).numpy()
+    tail = np.stack(sharding.pad_block(local, k + (total - blk * world)))[:, k:]
+    allsrc = np.concatenate([torch.cat(gathered, dim=1).numpy(), tail], axis=1)
+    assert allsrc.shape[1] == total
     P = oracle.port()
     got = P.points_on_points("v2", oracle.VELONLY, allsrc[0], allsrc[1], allsrc[2], allsrc[3], sx[lo:hi], sy[lo:hi], sr[lo:hi])
     want = P.points_on_points("v2", oracle.VELONLY, sx, sy, ss, sr, sx[lo:hi], sy[lo:hi], sr[lo:hi])
