@@ -153,6 +153,19 @@ __device__ __forceinline__ void tile_sum(const float4* __restrict__ s, const flo
           pair_accumulate<RES, false>(part[k], str, K, Bb, dxk[k], dyk[k], d2);
         }
       }
+    } else if constexpr (CORE == CORE_WL && UNI && !T::GRAD) {
+      // Winckelmans-Leonard velocity with one radius term for all R targets: r2 = ss K = ss (r + s2 r^2) = r (ss + (ss s2) r)
+      // with r = 1/D; ss*s2 is formed once per source pair, so a pair costs 8 lane-ops + 1 MUFU instead of 9
+      const float2 ss2 = mul2(str, rho);
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        const float2 dx = add2(tx[k], nsx);
+        const float2 dy = add2(ty[k], nsy);
+        const float2 r = rcp2(fma2(dy, dy, fma2(dx, dx, rho)));
+        const float2 r2 = mul2(r, fma2(ss2, r, str));
+        part[k][0] = fma2(r2, dy, part[k][0]);
+        part[k][1] = fma2(r2, dx, part[k][1]);
+      }
     } else {
 #pragma unroll
       for (int k = 0; k < R; ++k) {
