@@ -455,7 +455,9 @@ def test_find_vels_multi_collections(ctx, port):
     and on inert targets -- ONE call, against the reference's loop order (zero; every source in turn; finalize) done
     with the oracle; and with a single collection it is o2d_find_vels bit for bit."""
     fs = (0.7, -0.2)
-    vorts = [W.gaussian_blob(n, seed=40 + n, signed=True) for n in (1501, 0, 2333)] + [W.annulus_blobs(777, seed=3)]
+    empty = tuple(np.zeros(0, np.float32) for _ in range(4))
+    vorts = [W.gaussian_blob(1501, seed=41, signed=True), empty, W.gaussian_blob(2333, seed=42, signed=True),
+             W.annulus_blobs(777, seed=3)]
     vorts = [tuple(np.asarray(a, np.float32) for a in v) for v in vorts]
     pans = [W.circle_panels(143, radius=0.5, seed=1), W.circle_panels(61, radius=0.2, center=(1.1, 0.3), seed=2)]
     pans = [(p[0], p[1], p[2], p[3], p[4]) for p in pans]

@@ -23,7 +23,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=1_000_000)
 ap.add_argument("--panels", type=int, default=20_000)
 ap.add_argument("--cpu-targets", type=int, default=4096)
-ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r01_path_table.md"))
+ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r02_path_table.md"))
 args = ap.parse_args()
 
 ctx = o2d.Context(0)
@@ -278,7 +278,7 @@ add("points_status (circulation, impulse, max strength)", "ElementBase.h:362-394
     float(n), sec, err, note="GPU time includes the 4-float result read-back; CPU = C restatement, one thread; the reference sums serially in float32, the GPU in float64 (fixed order)")
 
 hdr = [
-    f"# Every kernel of the path at full size: B200 vs the reference's CPU implementation (round 1)",
+    f"# Every kernel of the path at full size: B200 vs the reference's CPU implementation (round 2)",
     "",
     f"`python tools/path_table.py --n {n} --panels {args.panels}` on one B200 ({info['sm_count']} SMs, {info['sm_clock_mhz']} MHz); "
     f"device-resident inputs, time = the pair kernel's own CUDA events on the launching stream (library timers), mean of 3 launches "

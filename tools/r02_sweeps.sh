@@ -9,6 +9,7 @@ if [ "$N" != 1 ] && [ "$N" != 8 ] && [ "$N" != 2 ]; then
   $TR ${N:+--master-port 29521} bench.py --gpus $N --steps 6 --warmup 3 > gpurun_out/r02_bench_n$N.json 2> gpurun_out/r02_bench_n$N.err
 fi
 if [ "$N" != 1 ]; then
+  $TR --master-port 29524 tools/multi_gpu_check.py > gpurun_out/r02_multi_gpu_check_n$N.txt 2>&1; tail -4 gpurun_out/r02_multi_gpu_check_n$N.txt
   $TR --master-port 29522 bench.py --gpus $N --workload c5 --scaling strong $OPT > gpurun_out/r02_c5_strong_n$N.json 2> gpurun_out/r02_c5_strong_n$N.err
   $TR --master-port 29523 bench.py --gpus $N --workload c5 --particles 5931642 --scaling weak $OPT > gpurun_out/r02_c5_weak_n$N.json 2> gpurun_out/r02_c5_weak_n$N.err
 else
