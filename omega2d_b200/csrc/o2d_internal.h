@@ -92,9 +92,11 @@ constexpr int pp_unroll(int core, int res, bool fine) {
 }
 // threads per CTA.  Coarse configuration: the 16-warp kernels run as ONE 512-thread CTA per SM with one equal run
 // each; the 24-warp kernels as three 256-thread CTAs with short runs (measured as one 768-thread CTA: EXP 10.5
-// against 11.0 pairs/clk/SM, V3 7.2 against 7.3).  See pp_plan (o2d_api.cu).
+// against 11.0 pairs/clk/SM, V3 7.2 against 7.3).  The V2 core also keeps 256-thread CTAs (two per SM, short runs):
+// equal at 1M particles, but 6 % faster than one 512-thread CTA at 100k-400k (V2 uniform, 200k: 10.88 vs 11.52 ms).
+// See pp_plan (o2d_api.cu).
 constexpr int pp_threads(int core, int res, bool fine) {
-  return fine ? kFineThreads : (pp_min_warps(core, res, false) == 16 ? 512 : kThreads);
+  return fine ? kFineThreads : ((pp_min_warps(core, res, false) == 16 && core != CORE_V2) ? 512 : kThreads);
 }
 inline int res_targets_per_thread(int core, int res, bool fine = false) { return pp_targets(res == RES_VORT ? CORE_RM : core, res, fine); }
 // targets per block of the (core, res) kernel
