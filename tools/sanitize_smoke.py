@@ -25,6 +25,11 @@ if PART == "tiny":
             want = P.points_on_points_grad(core, sx[:700], sy[:700], ss[:700], sr[:700], tx[:300], ty[:300], tr[:300]) if res == o2d.VELANDGRAD \
                 else P.points_on_points(core, res, sx[:700], sy[:700], ss[:700], sr[:700], tx[:300], ty[:300], tr[:300])
             assert W.rel_err(got[:2], want[:2]) < 1e-5
+    # runs that cross target-block boundaries and stage rings that wrap (9 000 sources = 18 coarse tiles, 7 000 targets)
+    bx, by, bs, br = W.gaussian_blob(9000, seed=5)
+    got = ctx.points_on_points_np("rm", o2d.VELONLY, bx, by, bs, br, bx[:7000], by[:7000], br[:7000])
+    want = P.points_on_points("rm", o2d.VELONLY, bx, by, bs, br, bx[:7000], by[:7000], br[:7000])
+    assert W.rel_err(got, want) < 1e-5
     print("SANITIZE_SMOKE OK (tiny)")
     sys.exit(0)
 for core in (o2d.CORES if PART in ("all", "pp") else ()):
@@ -68,6 +73,18 @@ want = P.find_vels("v2", o2d.VELANDVORT, vort, (nx, ny, idx, vs, sps), vort[0], 
 assert W.rel_err(got[:2], want[:2]) < 1e-5
 for order in (1, 2, 3):
     ctx.advect_np("rm", order, *vort, 0.01, (nx, ny, idx, vs, sps), (1.0, 0.0))
+# round 2: several collections in one call, the step with a body (solve callback), the sharded entry on one rank
+got = ctx.find_vels_multi_np("v2", o2d.VELONLY, [vort, W.annulus_blobs(333, seed=9)], [(nx, ny, idx, vs, sps), (nx * 0.5 + 2.0, ny * 0.5, idx, vs, None)],
+                             vort[0], vort[1], vort[3], (1.0, 0.0))
+assert np.isfinite(got[0]).all()
+near = W.annulus_blobs(1500, rin=0.495, rout=0.8, seed=4)
+for order in (1, 2, 3):
+    out = ctx.advect_bodies_np("v2", order, *near, (nx, ny, idx, np.zeros_like(vs), np.zeros_like(vs)), area, (snx, sny),
+                               lambda stage, t, pu, pv: (-(pu * ttx + pv * tty), -(pu * snx + pv * sny)), 0.02, 0.02191, (1.0, 0.0))
+    assert np.isfinite(out[0]).all() and np.isfinite(out[4]).all()
+so = [np.zeros(nt, np.float32) for _ in range(3)]
+ctx.points_on_points_sharded("exp", o2d.VELANDVORT, o2d.MEM_HOST, ns, ns + 5, sx, sy, ss, sr, nt, tx + 3.0, ty, tr, so[0], so[1], so[2])
+assert W.rel_err(so[:2], P.points_on_points("exp", o2d.VELANDVORT, sx, sy, ss, sr, tx + 3.0, ty, tr)[:2]) < 1e-5
 x, y, s, r = W.c1_speedtest(3000)
 u, v = np.zeros_like(x), np.zeros_like(x)
 ctx.advect("v2", 2, o2d.MEM_HOST, x.size, x.copy(), y.copy(), s, r, u, v, dt=0.005, nsteps=3)
