@@ -175,7 +175,11 @@ def run_reference_arm(args, wl, n):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32 pair terms, f64 accumulation",
         "data": "synthetic",
-        "config": {"workload": wl["desc"], "particles": n, "core": wl["core"],
+        # same keys as our arm's config (the driver compares the two)
+        "config": {"workload": wl["desc"], "particles": n, "particles_per_gpu": sharding.block_size(n, max(1, int(os.environ.get("WORLD_SIZE", "1")))),
+                   "core": wl["core"], "results": wl["results"],
+                   "pairs_per_step": float(n) * float(n) + (float(n) * wl["panels"][0] * wl["panels"][1] if wl.get("panels") else 0.0),
+                   "l2": "n/a (CPU arm)", "parallelism": "OpenMP over targets on the host cores (rank 0 only)",
                    "sample": f"{count} strided targets x {n} sources per step"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": f"{count} strided targets x all {n} sources per step, OpenMP on all host cores, USE_VC off"},
@@ -722,6 +726,7 @@ def run_ours(args, wl, n1):
         "dtype": "f32 pair terms, f64 accumulation", "data": "synthetic",
         "config": {"workload": wl["desc"], "particles": n, "particles_per_gpu": nblock, "core": core,
                    "results": results, "pairs_per_step": pairs_per_step, "l2": "flushed between timed iterations (256 MB write)",
+                   "sample": "every target x every source, every step",
                    "parallelism": "single GPU" if world == 1 else f"targets sharded in {world} contiguous blocks, "
                                   "sources all-gathered (NCCL) once per step"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": cnt["launches"],

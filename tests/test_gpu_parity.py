@@ -520,3 +520,30 @@ def test_sharded_entry_with_empty_block_and_exp_gradients(ctx, port):
         want = ctx.points_on_points_np(core, o2d.VELANDVORT, sx, sy, ss, sr, tx, ty, tr)
         for a, b in zip(got, want):
             assert W.rel_err(a, b) < 1e-6
+
+
+def test_find_vels_multi_device_memory_equals_host_path(ctx):
+    """o2d_find_vels_multi with device pointers in the views (O2D_MEM_DEVICE) gives the bits of the host-array path."""
+    import ctypes as C
+    import torch
+    dev = torch.device("cuda:0")
+    fs = (0.3, 0.1)
+    vorts = [W.gaussian_blob(3001, seed=5, signed=True), W.annulus_blobs(1200, seed=6)]
+    pan = W.circle_panels(143, radius=0.5, seed=1)
+    tx, ty, _, tr = W.gaussian_blob(2500, seed=7, sigma=0.7)
+    host = ctx.find_vels_multi_np("v2", o2d.VELANDVORT, vorts, [pan], tx, ty, tr, fs)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    dv = [[T(a) for a in v] for v in vorts]
+    dp = [T(pan[0]), T(pan[1]), T(pan[2].astype(np.int32)), T(pan[3]), T(pan[4])]
+    dt = [T(tx), T(ty), T(tr)]
+    out = [torch.empty(tx.size, device=dev) for _ in range(3)]
+    pv = (o2d.PointsView * 2)(*[o2d.PointsView(v[0].numel(), *[t.data_ptr() for t in v]) for v in dv])
+    qv = (o2d.PanelsView * 1)(o2d.PanelsView(pan[3].size, pan[0].size, *[t.data_ptr() for t in dp]))
+    rc = ctx.lib.o2d_find_vels_multi(ctx._h, o2d.CORE_ID["v2"], o2d.VELANDVORT, o2d.MEM_DEVICE, 2, pv, 1, qv, tx.size,
+                                     C.c_void_p(dt[0].data_ptr()), C.c_void_p(dt[1].data_ptr()), C.c_void_p(dt[2].data_ptr()),
+                                     C.c_void_p(out[0].data_ptr()), C.c_void_p(out[1].data_ptr()), C.c_void_p(out[2].data_ptr()),
+                                     fs[0], fs[1])
+    assert rc == o2d.OK, ctx.lib.o2d_last_error()
+    ctx.synchronize()
+    for a, b in zip(out, host):
+        np.testing.assert_array_equal(a.cpu().numpy(), b)
