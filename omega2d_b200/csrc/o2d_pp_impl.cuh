@@ -238,6 +238,9 @@ pp_kernel(const PPArgs a) {
 #pragma unroll
     for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); done[s] = 0; }
     mbar_fence_init();
+  }
+  __syncthreads();   // the only CTA-wide barrier: the mbarriers exist before anyone polls them
+  if (tid == 0) {    // fill the ring; the other warps are already fetching their targets
 #pragma unroll
     for (int s = 0; s < NS; ++s)
       if (s < nsteps) {
@@ -245,7 +248,6 @@ pp_kernel(const PPArgs a) {
         tma_load_1d(smem_raw + (size_t)s * TILE_BYTES, a.packed + (size_t)((tile + s) % a.ntiles) * TILE, TILE_BYTES, &full[s]);
       }
   }
-  __syncthreads();   // the only CTA-wide barrier: the mbarriers exist before anyone polls them
 
   int step = 0;   // steps done by this warp; stage = step % NS, mbarrier phase = (step / NS) & 1
   for (int seg = 0; step < nsteps; ++seg, ++block, tile = 0) {
