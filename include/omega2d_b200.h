@@ -387,8 +387,10 @@ int o2d_comm_destroy(o2d_context* ctx);
 /*
  * Sharded points-on-points: this rank owns ns_local source particles (its block of the
  * global set) and nt target points.  Each rank's packed source block is replicated to every
- * rank with ONE ncclAllGather over NVLink (16 B per particle), overlapped with the sum over
- * the rank's own block; outputs stay on the owning rank.  ns_block is the per-rank block
+ * rank with ONE in-place ncclAllGather over NVLink (16 B per particle) on the launching stream,
+ * and the gathered array is summed by the same single launch as on one GPU (the gather is
+ * ~1e-4 of the evaluation; a launch that owns the whole device is worth more than hiding it);
+ * outputs stay on the owning rank.  ns_block is the per-rank block
  * capacity agreed by all ranks (>= every rank's ns_local, e.g. ceil(N/nranks)).
  * Same argument meaning as o2d_points_on_points otherwise.
  */

@@ -480,6 +480,21 @@ int o2dref_affect_bricks(int from_panels, int results,
 }
 
 
+// reference Surfaces::represent_as_particles (src/Surfaces.h:830-873): the particle version of the panels that
+// panels_affect_panels (offset 1e-4, ips -1) and the diffusion step use.  Returns the number of points written.
+int o2dref_represent_as_particles(int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx, const float* vs,
+                                  float offset, float ips, int cap, float* px, float* py, float* pval) {
+  StdoutMute mute;
+  std::vector<float> z((size_t)np, 0.0f);
+  Surfaces<float> s = make_surfaces(np, nnodes, nx, ny, idx, vs, z.data());
+  const ElementPacket<float> pk = s.represent_as_particles(offset, ips);
+  const int n = (int)pk.nelem;
+  if (n > cap) return -n;
+  for (int i = 0; i < n; ++i) { px[i] = pk.x[2*i]; py[i] = pk.x[2*i+1]; pval[i] = pk.val[i]; }
+  return n;
+}
+
+
 // ---- BEM coefficients -----------------------------------------------------------------------------
 // reference panels_on_panels_coeff<float> (src/Coefficients.h:155-573) called on the reference's
 // own Surfaces.  same != 0: one surface acting on itself (self-influence diagonal).  The reference
