@@ -152,6 +152,38 @@ __device__ __forceinline__ void panel_far2(float2 ex, float2 ey, float2 Hx, floa
   ri = fma2(zx, qi, mul2(zy, qr));
 }
 
+// The same with the series length chosen per warp: beyond |zeta|^2 < kVeryFarZeta2 (targets further than ~6 panel lengths
+// from the panel centre: nearly every pair of a body seen from the flow) the w^3/7 term is below 4.3e-8 relative too and is
+// dropped -- 22 instead of 26 lane-ops.  thr2 = |H|^2 / kVeryFarZeta2 per lane; the choice is one warp vote, so the
+// branch is uniform.  Lanes that fail even kFarZeta2 are the caller's business, as with panel_far2.
+constexpr float kVeryFarZeta2 = 0.0066f;
+__device__ __forceinline__ void panel_far2v(float2 ex, float2 ey, float2 Hx, float2 Hy, float2 thr2,
+                                            float2& rr, float2& ri, float2& e2) {
+  e2 = fma2(ex, ex, mul2(ey, ey));
+  const float2 r = rcp2(e2);
+  const float2 qx = mul2(ex, r), qy = mul2(ey, r);
+  const float2 zx = fma2(Hx, qx, mul2(Hy, qy));            // zeta' = H conj(e) / |e|^2
+  const float2 zy = fma2(Hy, qx, neg2(mul2(Hx, qy)));
+  const float2 wx = fma2(zx, zx, neg2(mul2(zy, zy)));      // w = zeta'^2
+  const float2 wy = mul2(add2(zx, zx), zy);
+  float2 qr, qi;
+  if (__all_sync(0xffffffffu, e2.x > thr2.x && e2.y > thr2.y)) {
+    const float2 tr = fma2(f2(0.2f), wx, f2(1.0f / 3.0f));  // 1/3 + w/5
+    const float2 ti = mul2(f2(0.2f), wy);
+    qr = fma2(tr, wx, fma2(neg2(ti), wy, f2(1.0f)));
+    qi = fma2(tr, wy, mul2(ti, wx));
+  } else {
+    float2 ar = fma2(f2(1.0f / 7.0f), wx, f2(0.2f));       // Horner in the complex w
+    float2 ai = mul2(f2(1.0f / 7.0f), wy);
+    const float2 tr = fma2(ar, wx, fma2(neg2(ai), wy, f2(1.0f / 3.0f)));
+    const float2 ti = fma2(ar, wy, mul2(ai, wx));
+    qr = fma2(tr, wx, fma2(neg2(ti), wy, f2(1.0f)));
+    qi = fma2(tr, wy, mul2(ti, wx));
+  }
+  rr = fma2(zx, qr, neg2(mul2(zy, qi)));
+  ri = fma2(zx, qi, mul2(zy, qr));
+}
+
 // ---- radius terms ----------------------------------------------------------------------------
 // Per-element radius term the cores add to the distance term: r^2 for RM/EXP/WL, r^4 for V2,
 // r^6 for V3, formed with the reference's own float products (s2 = sr*sr; s2*s2; s2*s2*s2,

@@ -28,10 +28,10 @@ namespace o2d {
 // src/Influence.h:561-562) ---------------------------------------------------------------------------
 // One thread per PAIR of panels (A = 2q, B = 2q+1); 4 float4 per pair so that every operand of the
 // packed-lane arithmetic is one 8-byte half of an LDS.128:
-//   {x0A x0B y0A y0B} {HxA HxB HyA HyB} {aA aB bA bB} {thrA thrB - -}
+//   {x0A x0B y0A y0B} {HxA HxB HyA HyB} {aA aB bA bB} {thrA thrB thr2A thr2B}
 // H = -p/2 (p = node1 - node0), a,b = the strength-weighted unit tangent of the header comment times -2
 // (panel_far2 returns -ustar/2, -vstar/2), thr = |H|^2 / kFarZeta2: a target with |t - centre|^2 <= thr takes
-// the general panel_pair().
+// the general panel_pair(); thr2 = |H|^2 / kVeryFarZeta2: beyond it the shorter series of panel_far2v is exact enough.
 __global__ void __launch_bounds__(256)
 pack_panels_kernel(int np, int j0, const float* __restrict__ nx, const float* __restrict__ ny,
                    const uint32_t* __restrict__ idx, const float* __restrict__ vs,
@@ -57,7 +57,7 @@ pack_panels_kernel(int np, int j0, const float* __restrict__ nx, const float* __
   packed[4 * q]     = make_float4(x0[0], x0[1], y0[0], y0[1]);
   packed[4 * q + 1] = make_float4(hx[0], hx[1], hy[0], hy[1]);
   packed[4 * q + 2] = make_float4(a[0], a[1], b[0], b[1]);
-  packed[4 * q + 3] = make_float4(thr[0], thr[1], 0.0f, 0.0f);
+  packed[4 * q + 3] = make_float4(thr[0], thr[1], thr[0] * (kFarZeta2 / kVeryFarZeta2), thr[1] * (kFarZeta2 / kVeryFarZeta2));
 }
 
 cudaError_t launch_pack_panels(int np, const float* nx, const float* ny, const uint32_t* idx,
@@ -124,7 +124,7 @@ panels_on_points_kernel(const PanelArgs a) {
         const float2 ex = add2(add2(f2(tx[k]), neg2(f2(P.x, P.y))), Hx);
         const float2 ey = add2(add2(f2(ty[k]), neg2(f2(P.z, P.w))), Hy);
         float2 rr, ri, e2;
-        panel_far2(ex, ey, Hx, Hy, rr, ri, e2);
+        panel_far2v(ex, ey, Hx, Hy, f2(T.z, T.w), rr, ri, e2);
         const bool na = !(e2.x > T.x), nb = !(e2.y > T.y);   // also true for NaN
         if (__any_sync(0xffffffffu, na || nb))
           near_fix(na, nb, P.x, P.z, H.x, H.z, P.y, P.w, H.y, H.w, tx[k], ty[k], rr, ri);
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(kPtPanThreads)
 points_on_panels_kernel(const PtPanArgs a) {
   __shared__ float4 s[kTile];   // one tile of packed particle pairs (16 KiB)
   const int tid = threadIdx.x;
-  float x0[kPtPanPPT], y0[kPtPanPPT], px[kPtPanPPT], py[kPtPanPPT], thr[kPtPanPPT];
+  float x0[kPtPanPPT], y0[kPtPanPPT], px[kPtPanPPT], py[kPtPanPPT], thr[kPtPanPPT], thr2[kPtPanPPT];
   float2 Hx[kPtPanPPT], Hy[kPtPanPPT];
   bool ok[kPtPanPPT];
 #pragma unroll
@@ -215,6 +215,7 @@ points_on_panels_kernel(const PtPanArgs a) {
     // the same zeta'; a packed lane pair is TWO PARTICLES against this thread's panel
     Hx[k] = f2(0.5f * px[k]); Hy[k] = f2(0.5f * py[k]);
     thr[k] = (Hx[k].x * Hx[k].x + Hy[k].x * Hy[k].x) * (1.0f / kFarZeta2);
+    thr2[k] = thr[k] * (kFarZeta2 / kVeryFarZeta2);
   }
   const int tile_begin = blockIdx.y * a.tiles_per_chunk;
   const int tile_end = min(tile_begin + a.tiles_per_chunk, a.ntiles);
@@ -239,7 +240,7 @@ points_on_panels_kernel(const PtPanArgs a) {
         const float2 ex = add2(add2(f2(A.x, A.y), f2(x0[k])), Hx[k]);
         const float2 ey = add2(add2(f2(A.z, A.w), f2(y0[k])), Hy[k]);
         float2 rr, ri, e2;
-        panel_far2(ex, ey, Hx[k], Hy[k], rr, ri, e2);
+        panel_far2v(ex, ey, Hx[k], Hy[k], f2(thr2[k]), rr, ri, e2);
         const bool na = !(e2.x > thr[k]), nb = !(e2.y > thr[k]);
         if (__any_sync(0xffffffffu, na || nb)) {
           float us, vs;
