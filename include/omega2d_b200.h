@@ -224,6 +224,10 @@ int o2d_advect_steps(o2d_context* ctx, int core, int order, int mem,
  *       stage = 0, 1, 2; time = the stage time the reference passes to solve_bem.
  *   area, snx, sny: panel lengths and unit normals (Surfaces::get_area / get_norm); cutoff_mult = 0.5/sqrt(2 pi) and
  *       ips as for o2d_clear_inner_layer.  Bodies do not move inside a step (fixed or externally transformed panels).
+ *   nf, fx, fy, fu, fv: an optional collection of inert Lagrangian field points (tracers; nf = 0: none).  The reference
+ *       evaluates and moves them alongside the particles in every stage ("find_vels(_fs, _vort, _bdry, _fldpt)",
+ *       src/Convection.h:242, the interim_fldpt copies :343-348) and clears them out of the body too; here they ride
+ *       along on the device: positions advance in place, fu,fv receive what the reference leaves in their velocity arrays.
  * Host arrays only (the callback runs on the host).  x,y are advanced in place; u,v as for o2d_advect.
  */
 typedef int (*o2d_bem_solve_fn)(void* user, int stage, double time, int np, const float* pu, const float* pv,
@@ -233,6 +237,7 @@ int o2d_advect_bodies(o2d_context* ctx, int core, int order, int mem,
                       int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
                       const float* area, const float* snx, const float* sny, float* pvs, float* pss,
                       double fsx, double fsy, double time, double dt, float cutoff_mult, float ips,
+                      int nf, float* fx, float* fy, float* fu, float* fv,
                       o2d_bem_solve_fn solve, void* user);
 
 /*

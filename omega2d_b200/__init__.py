@@ -112,7 +112,7 @@ def load_library() -> C.CDLL:
     lib.o2d_find_vels_multi.argtypes = [vp, i, i, i, i, C.POINTER(PointsView), i, C.POINTER(PanelsView),
                                         i, vp, vp, vp, vp, vp, vp, d, d]
     lib.o2d_advect_bodies.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp,
-                                      d, d, d, d, C.c_float, C.c_float, BEM_SOLVE_FN, vp]
+                                      d, d, d, d, C.c_float, C.c_float, i, vp, vp, vp, vp, BEM_SOLVE_FN, vp]
     lib.o2d_panels_on_panels_coeff.argtypes = [vp, i, i, i, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp,
                                                i, i, C.c_longlong, vp]
     lib.o2d_clear_inner_layer.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp, i, vp, vp, C.c_float, C.c_float,
@@ -521,9 +521,10 @@ class Context:
         return x, y, u, v
 
     def advect_bodies_np(self, core, order, x, y, s, r, panels, area, normals, solve, dt, ips, fs=(0.0, 0.0), time=0.0,
-                         cutoff_mult=None):
+                         cutoff_mult=None, fldpt=None):
         """One convection step with bodies (o2d_advect_bodies).  panels = (nx, ny, idx, vs, ss|None); normals = (snx, sny);
-        solve(stage, time, pu, pv) -> (vs, ss).  Returns (x, y, u, v, vs, ss) after the step."""
+        solve(stage, time, pu, pv) -> (vs, ss); fldpt = (fx, fy) inert tracers or None.  Returns (x, y, u, v, vs, ss) after
+        the step, followed by (fx, fy, fu, fv) when tracers were given."""
         core = CORE_ID[core] if isinstance(core, str) else int(core)
         x, y = np.array(x, np.float32), np.array(y, np.float32)
         s, r, area = map(_f32, (s, r, area))
@@ -536,11 +537,18 @@ class Context:
         if cutoff_mult is None:
             cutoff_mult = np.float32(0.5 / np.sqrt(2.0 * np.pi))   # src/Convection.h:306
         cb = bem_solve_callback(solve)
+        nf = 0
+        fx = fy = fu = fv = None
+        if fldpt is not None:
+            fx, fy = np.array(fldpt[0], np.float32), np.array(fldpt[1], np.float32)
+            nf = fx.size
+            fu, fv = np.empty(nf, np.float32), np.empty(nf, np.float32)
         self._check(self.lib.o2d_advect_bodies(
             self._h, core, int(order), MEM_HOST, x.size, _ptr(x), _ptr(y), _ptr(s), _ptr(r), _ptr(u), _ptr(v),
             pvs.size, nx.size, _ptr(nx), _ptr(ny), _ptr(idx), _ptr(area), _ptr(snx), _ptr(sny), _ptr(pvs), _ptr(pss),
-            float(fs[0]), float(fs[1]), float(time), float(dt), float(cutoff_mult), float(ips), cb, None))
-        return x, y, u, v, pvs, pss
+            float(fs[0]), float(fs[1]), float(time), float(dt), float(cutoff_mult), float(ips),
+            nf, _ptr(fx), _ptr(fy), _ptr(fu), _ptr(fv), cb, None))
+        return (x, y, u, v, pvs, pss) if fldpt is None else (x, y, u, v, pvs, pss, fx, fy, fu, fv)
 
     def panels_on_panels_coeff_np(self, src, sarea, targ, tbases, both=True, same=False, ld=None):
         """src/targ = (nx, ny, idx); tbases = (ttx, tty, tnx, tny, tarea).  Returns (cols, ld) float32."""

@@ -467,7 +467,8 @@ struct BodyDev {
 };
 
 int stage_derivs(o2d_context* c, int core, int n, const float* x, const float* y, const float* s, const float* r,
-                 float* u, float* v, BodyDev& b, float* h_pu, float* h_pv, float* h_vs, float* h_ss,
+                 float* u, float* v, int nf, const float* fx, const float* fy, float* fu, float* fv,
+                 BodyDev& b, float* h_pu, float* h_pv, float* h_vs, float* h_ss,
                  double fsx, double fsy, int stage, double time, o2d_bem_solve_fn solve, void* user) {
   const int np = b.pan.np;
   int rc;
@@ -491,8 +492,10 @@ int stage_derivs(o2d_context* c, int core, int n, const float* x, const float* y
     if (b.ss) up.add(b.ss, h_ss, (size_t)np);
     if ((rc = up.upload())) return rc;
   }
-  // find_vels(fs, vort, bdry, vort)
-  return find_vels_device(c, core, RES_U, n, x, y, s, r, b.pan, n, x, y, r, u, v, nullptr, fsx, fsy);
+  // find_vels(fs, vort, bdry, vort); find_vels(fs, vort, bdry, fldpt)   (src/Convection.h:241-242)
+  if ((rc = find_vels_device(c, core, RES_U, n, x, y, s, r, b.pan, n, x, y, r, u, v, nullptr, fsx, fsy))) return rc;
+  if (nf > 0) return find_vels_device(c, core, RES_U, n, x, y, s, r, b.pan, nf, fx, fy, nullptr, fu, fv, nullptr, fsx, fsy);
+  return O2D_OK;
 }
 
 }  // namespace
@@ -502,8 +505,11 @@ extern "C" int o2d_advect_bodies(o2d_context* c, int core, int order, int mem,
                                  int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx,
                                  const float* area, const float* snx, const float* sny, float* pvs, float* pss,
                                  double fsx, double fsy, double time, double dt, float cutoff_mult, float ips,
+                                 int nf, float* fx, float* fy, float* fu, float* fv,
                                  o2d_bem_solve_fn solve, void* user) {
   if (int rc = o2d_check_common(c, mem)) return rc;
+  if (nf < 0) return fail(O2D_ERR_INVALID, "negative count");
+  if (nf > 0 && (!fx || !fy || !fu || !fv)) return fail(O2D_ERR_INVALID, "NULL field-point array");
   if (mem != O2D_MEM_HOST)
     return fail(O2D_ERR_UNSUPPORTED, "o2d_advect_bodies takes host arrays (the solve callback runs on the host every stage)");
   if (core < 0 || core > 4) return fail(O2D_ERR_INVALID, "unknown core %d", core);
@@ -524,7 +530,12 @@ extern "C" int o2d_advect_bodies(o2d_context* c, int core, int order, int mem,
   CU(c->adv.reserve(8 * padded_floats(n)));
   CU(c->hpan.reserve(2 * padded_floats(nnodes) + 7 * padded_floats(np)));
   CU(c->hidx.reserve((size_t)2 * np * sizeof(uint32_t)));
-  Stager S(c, &c->hsrc), O(c, &c->hout), A(c, &c->adv), Pn(c, &c->hpan);
+  CU(c->htgt.reserve(12 * padded_floats(nf) + 256));
+  Stager S(c, &c->hsrc), O(c, &c->hout), A(c, &c->adv), Pn(c, &c->hpan), F(c, &c->htgt);
+  // field points (inert Lagrangian tracers): positions, velocities and the intermediate stages
+  float *dfx = F.take(nf), *dfy = F.take(nf), *dfu = F.take(nf), *dfv = F.take(nf);
+  float *fx1 = F.take(nf), *fy1 = F.take(nf), *fu1 = F.take(nf), *fv1 = F.take(nf);
+  float *fx2 = F.take(nf), *fy2 = F.take(nf), *fu2 = F.take(nf), *fv2 = F.take(nf);
   float *dx = S.take(n), *dy = S.take(n), *ds = S.take(n), *dr = S.take(n);
   float *du = O.take(n), *dv = O.take(n);
   float *x1 = A.take(n), *y1 = A.take(n), *u1 = A.take(n), *v1 = A.take(n);
@@ -539,6 +550,11 @@ extern "C" int o2d_advect_bodies(o2d_context* c, int core, int order, int mem,
     bp.add(dx, x, n); bp.add(dy, y, n); bp.add(ds, s, n); bp.add(dr, r, n);
     bb.add(dnx, nx, nnodes); bb.add(dny, ny, nnodes); bb.add(darea, area, np); bb.add(dsnx, snx, np); bb.add(dsny, sny, np);
     if ((rc = bp.upload()) || (rc = bb.upload())) return rc;
+    if (nf > 0) {
+      HostBatch bf(c);
+      bf.add(dfx, fx, nf); bf.add(dfy, fy, nf);
+      if ((rc = bf.upload())) return rc;
+    }
   }
   if ((rc = o2d_h2d_bytes(c, c->hidx.p, idx, (size_t)2 * np * sizeof(uint32_t)))) return rc;
   b.pan.np = np; b.pan.nx = dnx; b.pan.ny = dny; b.pan.idx = c->hidx.as<uint32_t>(); b.pan.vs = b.vs; b.pan.ss = b.ss;
@@ -547,46 +563,53 @@ extern "C" int o2d_advect_bodies(o2d_context* c, int core, int order, int mem,
   std::vector<float> hbuf(2 * (size_t)np);
   float* h_pu = hbuf.data();
   float* h_pv = h_pu + np;
-  const int nb = (n + 255) / 256;
+  const int nb = (n + 255) / 256, nbf = (nf + 255) / 256;
   const float fdt = (float)dt;   // "(S)_dt" in ElementBase::move
-  auto derivs = [&](int stage, double t, const float* px, const float* py, float* pu_, float* pv_) {
-    return stage_derivs(c, core, n, px, py, ds, dr, pu_, pv_, b, h_pu, h_pv, pvs, pss, fsx, fsy, stage, t, solve, user);
+  auto derivs = [&](int stage, double t, const float* px, const float* py, float* pu_, float* pv_,
+                    const float* qx, const float* qy, float* qu, float* qv) {
+    return stage_derivs(c, core, n, px, py, ds, dr, pu_, pv_, nf, qx, qy, qu, qv, b, h_pu, h_pv, pvs, pss, fsx, fsy, stage, t,
+                        solve, user);
   };
   if ((rc = o2d_cil_prepare(c, np, nnodes, dnx, dny, b.pan.idx, dsnx, dsny))) return rc;   // the body is fixed within the step
-  auto clear = [&](float* px, float* py) { return o2d_cil_run(c, 1, n, px, py, cutoff_mult, ips, nullptr); };
-  if ((rc = derivs(0, time, dx, dy, du, dv))) return rc;
+  auto clear = [&](int m, float* px, float* py) { return m > 0 ? o2d_cil_run(c, 1, m, px, py, cutoff_mult, ips, nullptr) : O2D_OK; };
+  // ElementBase::move for the particles and, with the same weights, for the field points
+  auto move1 = [&](const float* xi, const float* yi, float* xo, float* yo, const float* u_, const float* v_,
+                   const float* fxi, const float* fyi, float* fxo, float* fyo, const float* fu_, const float* fv_, float sdt) {
+    move1_kernel<<<nb, 256, 0, c->stream>>>(n, xi, yi, xo, yo, u_, v_, sdt, 1.0);
+    c->launches++;
+    if (nf > 0) { move1_kernel<<<nbf, 256, 0, c->stream>>>(nf, fxi, fyi, fxo, fyo, fu_, fv_, sdt, 1.0); c->launches++; }
+    return cudaGetLastError();
+  };
+  auto move23 = [&](const float* ua, const float* va, const float* ub, const float* vb, const float* fua, const float* fva,
+                    const float* fub, const float* fvb, double w1, double w2, double w3) {
+    move23_kernel<<<nb, 256, 0, c->stream>>>(n, dx, dy, du, dv, ua, va, ub, vb, fdt, w1, w2, w3);
+    c->launches++;
+    if (nf > 0) { move23_kernel<<<nbf, 256, 0, c->stream>>>(nf, dfx, dfy, dfu, dfv, fua, fva, fub, fvb, fdt, w1, w2, w3); c->launches++; }
+    return cudaGetLastError();
+  };
+  if ((rc = derivs(0, time, dx, dy, du, dv, dfx, dfy, dfu, dfv))) return rc;
   if (order == 1) {
     // advect_1st (src/Convection.h:277-308)
-    move1_kernel<<<nb, 256, 0, c->stream>>>(n, dx, dy, dx, dy, du, dv, fdt, 1.0);
-    CU(cudaGetLastError());
-    c->launches++;
-    if ((rc = clear(dx, dy))) return rc;
+    CU(move1(dx, dy, dx, dy, du, dv, dfx, dfy, dfx, dfy, dfu, dfv, fdt));
+    if ((rc = clear(n, dx, dy)) || (rc = clear(nf, dfx, dfy))) return rc;
   } else if (order == 2) {
     // advect_2nd_ralston (src/Convection.h:314-392)
     const double twothirds = 2.0 / 3.0;
-    move1_kernel<<<nb, 256, 0, c->stream>>>(n, dx, dy, x1, y1, du, dv, (float)(twothirds * dt), 1.0);
-    CU(cudaGetLastError());
-    c->launches++;
-    if ((rc = clear(x1, y1))) return rc;
-    if ((rc = derivs(1, time + twothirds * dt, x1, y1, u1, v1))) return rc;
-    move23_kernel<<<nb, 256, 0, c->stream>>>(n, dx, dy, du, dv, u1, v1, nullptr, nullptr, fdt, 0.25, 0.75, 0.0);
-    CU(cudaGetLastError());
-    c->launches++;
-    if ((rc = clear(dx, dy))) return rc;
+    CU(move1(dx, dy, x1, y1, du, dv, dfx, dfy, fx1, fy1, dfu, dfv, (float)(twothirds * dt)));
+    if ((rc = clear(n, x1, y1)) || (rc = clear(nf, fx1, fy1))) return rc;
+    if ((rc = derivs(1, time + twothirds * dt, x1, y1, u1, v1, fx1, fy1, fu1, fv1))) return rc;
+    CU(move23(u1, v1, nullptr, nullptr, fu1, fv1, nullptr, nullptr, 0.25, 0.75, 0.0));
+    if ((rc = clear(n, dx, dy)) || (rc = clear(nf, dfx, dfy))) return rc;
   } else {
     // advect_3rd (src/Convection.h:472-595)
-    move1_kernel<<<nb, 256, 0, c->stream>>>(n, dx, dy, x1, y1, du, dv, (float)(0.5 * dt), 1.0);
-    CU(cudaGetLastError());
-    if ((rc = clear(x1, y1))) return rc;
-    if ((rc = derivs(1, time + 0.5 * dt, x1, y1, u1, v1))) return rc;
-    move1_kernel<<<nb, 256, 0, c->stream>>>(n, dx, dy, x2, y2, u1, v1, (float)(0.75 * dt), 1.0);
-    CU(cudaGetLastError());
-    if ((rc = clear(x2, y2))) return rc;
-    if ((rc = derivs(2, time + 0.75 * dt, x2, y2, u2, v2))) return rc;
-    move23_kernel<<<nb, 256, 0, c->stream>>>(n, dx, dy, du, dv, u1, v1, u2, v2, fdt, 2.0 / 9.0, 3.0 / 9.0, 4.0 / 9.0);
-    CU(cudaGetLastError());
-    c->launches += 3;
-    if ((rc = clear(dx, dy))) return rc;
+    CU(move1(dx, dy, x1, y1, du, dv, dfx, dfy, fx1, fy1, dfu, dfv, (float)(0.5 * dt)));
+    if ((rc = clear(n, x1, y1)) || (rc = clear(nf, fx1, fy1))) return rc;
+    if ((rc = derivs(1, time + 0.5 * dt, x1, y1, u1, v1, fx1, fy1, fu1, fv1))) return rc;
+    CU(move1(dx, dy, x2, y2, u1, v1, dfx, dfy, fx2, fy2, fu1, fv1, (float)(0.75 * dt)));
+    if ((rc = clear(n, x2, y2)) || (rc = clear(nf, fx2, fy2))) return rc;
+    if ((rc = derivs(2, time + 0.75 * dt, x2, y2, u2, v2, fx2, fy2, fu2, fv2))) return rc;
+    CU(move23(u1, v1, u2, v2, fu1, fv1, fu2, fv2, 2.0 / 9.0, 3.0 / 9.0, 4.0 / 9.0));
+    if ((rc = clear(n, dx, dy)) || (rc = clear(nf, dfx, dfy))) return rc;
   }
   // ---- one download -------------------------------------------------------------------------------------------------------
   {
@@ -594,6 +617,11 @@ extern "C" int o2d_advect_bodies(o2d_context* c, int core, int order, int mem,
     bx.add(dx, x, n); bx.add(dy, y, n);
     bu.add(du, u, n); bu.add(dv, v, n);
     if ((rc = bx.download()) || (rc = bu.download())) return rc;
+    if (nf > 0) {
+      HostBatch bf(c);
+      bf.add(dfx, fx, nf); bf.add(dfy, fy, nf); bf.add(dfu, fu, nf); bf.add(dfv, fv, nf);
+      if ((rc = bf.download())) return rc;
+    }
   }
   if (int rc_ = o2d_finish_host(c)) return rc_;
   return O2D_OK;

@@ -119,9 +119,11 @@ void advect_particles(const int _order, const double _dt, const std::array<doubl
 // e.g. a lambda around vels_to_rhs_panels + BEM::set_rhs/solve/get_str.  The particles are uploaded once and
 // downloaded once per step; per stage 2*Np floats travel each way.  _surf's strength arrays end up holding the
 // strengths of the last stage, as after the reference's last solve_bem.
+// _fldpt: optional inert Lagrangian field points (tracers); evaluated, moved and cleared alongside the particles, as the
+// reference does with its _fldpt collections in every stage.
 template <class S, class SolveFn>
 void advect_with_body(const int _order, const double _time, const double _dt, const std::array<double,Dimensions>& _fs,
-                      const S _ips, Points<S>& _pts, Surfaces<S>& _surf, SolveFn&& _solve) {
+                      const S _ips, Points<S>& _pts, Surfaces<S>& _surf, SolveFn&& _solve, Points<S>* _fldpt = nullptr) {
   struct Tramp {
     static int call(void* user, int stage, double time, int np, const float* pu, const float* pv, float* vs, float* ss) {
       try {
@@ -144,6 +146,9 @@ void advect_with_body(const int _order, const double _time, const double _dt, co
                                     nrm[0].data(), nrm[1].data(), _surf.get_str().data(),
                                     _surf.have_src_str() ? _surf.get_src_str().data() : nullptr,
                                     _fs[0], _fs[1], _time, _dt, (float)(0.5 / std::sqrt(2.0 * M_PI)), (float)_ips,
+                                    _fldpt ? (int)_fldpt->get_n() : 0,
+                                    _fldpt ? _fldpt->get_pos()[0].data() : nullptr, _fldpt ? _fldpt->get_pos()[1].data() : nullptr,
+                                    _fldpt ? _fldpt->get_vel()[0].data() : nullptr, _fldpt ? _fldpt->get_vel()[1].data() : nullptr,
                                     &Tramp::call, &_solve),
                   "advect_with_body");
 }

@@ -414,7 +414,7 @@ class Ref:
                float(fs[0]), float(fs[1]), float(dt))
         assert rc == 0
         return x, y, u, v
-    def advect_bodies(self, order, x, y, s, r, panels, solve, dt, ips, fs=(0.0, 0.0), time=0.0):
+    def advect_bodies(self, order, x, y, s, r, panels, solve, dt, ips, fs=(0.0, 0.0), time=0.0, fldpt=None):
         """The reference's convection step with bodies (orchestration restated in ref_driver.cpp around the reference's own
         points_affect_panels / finalize_vels / find_vels pieces / Points::move / clear_inner_layer); the BEM linear solve is
         the caller's solve(stage, time, pu, pv) -> (vs, ss).  Returns (x, y, u, v, vs, ss)."""
@@ -429,12 +429,18 @@ class Ref:
         cb = bem_solve_callback(solve)
         f = self.lib.o2dref_advect_bodies
         f.argtypes = [C.c_int, C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, _fp, _fp, _up, _fp, _fp,
-                      C.c_double, C.c_double, C.c_double, C.c_double, C.c_float, C.c_void_p, C.c_void_p]
+                      C.c_double, C.c_double, C.c_double, C.c_double, C.c_float, C.c_int, _fp, _fp, _fp, _fp, C.c_void_p, C.c_void_p]
+        nf = 0
+        fx = fy = fu = fv = None
+        if fldpt is not None:
+            fx, fy = np.array(fldpt[0], np.float32), np.array(fldpt[1], np.float32)
+            nf = fx.size
+            fu, fv = np.zeros(nf, np.float32), np.zeros(nf, np.float32)
         rc = f(int(order), int(x.size), _f(x), _f(y), _f(s), _f(r), _f(u), _f(v), int(vs.size), int(nx.size), _f(nx), _f(ny),
                _u(idx), _f(vs), _f(ss), float(fs[0]), float(fs[1]), float(time), float(dt), float(ips),
-               C.cast(cb, C.c_void_p), None)
+               nf, _f(fx), _f(fy), _f(fu), _f(fv), C.cast(cb, C.c_void_p), None)
         assert rc == 0, rc
-        return x, y, u, v, vs, ss
+        return (x, y, u, v, vs, ss) if fldpt is None else (x, y, u, v, vs, ss, fx, fy, fu, fv)
 
     def panels_on_panels_coeff(self, src, targ=None):
         """The reference's own panels_on_panels_coeff<float> (always both strengths).  Returns

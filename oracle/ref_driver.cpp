@@ -368,7 +368,7 @@ int o2dref_advect(int order, int n, float* x, float* y, const float* s, const fl
 typedef int (*bem_solve_fn)(void* user, int stage, double time, int np, const float* pu, const float* pv, float* vs, float* ss);
 
 static int ref_derivs(const std::array<double,Dimensions>& fs, std::vector<Collection>& vort, std::vector<Collection>& bdry,
-                      int stage, double time, bem_solve_fn solve, void* user, float* vs, float* ss) {
+                      std::vector<Collection>& fldpt, int stage, double time, bem_solve_fn solve, void* user, float* vs, float* ss) {
   InfluenceVisitor<float,double> ivisitor = {ResultsType(velonly), ExecEnv(true, direct, cpu_x86)};
   Surfaces<float>& surf = std::get<Surfaces<float>>(bdry[0]);
   const int np = (int)surf.get_npanels();
@@ -381,54 +381,85 @@ static int ref_derivs(const std::array<double,Dimensions>& fs, std::vector<Colle
   auto& gv = surf.get_vort_str();
   for (int i = 0; i < np; ++i) gv[i] = vs[i];
   if (ss) { auto& gs = surf.get_src_str(); for (int i = 0; i < np; ++i) gs[i] = ss[i]; }
-  ref_find_vels(fs, vort, bdry, vort, velonly);
+  ref_find_vels(fs, vort, bdry, vort, velonly);       // find_derivs, src/Convection.h:241-242
+  ref_find_vels(fs, vort, bdry, fldpt, velonly);
   return 0;
 }
 
+// nf > 0: a collection of inert Lagrangian field points rides along, as _fldpt does in the reference's advect_*
 int o2dref_advect_bodies(int order, int n, float* x, float* y, const float* s, const float* r, float* u, float* v,
                          int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx, float* vs, float* ss,
-                         double fsx, double fsy, double time, double dt, float ips, bem_solve_fn solve, void* user) {
+                         double fsx, double fsy, double time, double dt, float ips,
+                         int nf, float* fx, float* fy, float* fu, float* fv, bem_solve_fn solve, void* user) {
   if (order < 1 || order > 3 || np <= 0) return -1;
   StdoutMute mute;
   const std::array<double,Dimensions> fs = {fsx, fsy};
   const float cutoff = 0.5/std::sqrt(2.0*M_PI);
-  std::vector<Collection> vort, bdry;
+  std::vector<Collection> vort, bdry, fldpt;
   vort.push_back(make_points(n, x, y, s, r));
   bdry.push_back(make_surfaces(np, nnodes, nx, ny, idx, vs, ss));
-  if (ref_derivs(fs, vort, bdry, 0, time, solve, user, vs, ss)) return -2;
+  if (nf > 0) {
+    std::vector<float> pf(2 * (size_t)nf);
+    for (int i = 0; i < nf; ++i) { pf[2*i] = fx[i]; pf[2*i+1] = fy[i]; }
+    fldpt.push_back(Points<float>(ElementPacket<float>(pf, std::vector<Int>(), std::vector<float>(), (size_t)nf, 0),
+                                  inert, lagrangian, nullptr, 0.0f));
+  }
+  auto move_all = [&](std::vector<Collection>& c, double sdt) {
+    for (auto& coll : c) std::visit([=](auto& elem) { elem.move(time, sdt, 1.0, elem); }, coll);
+  };
+  auto move2 = [&](std::vector<Collection>& c0, std::vector<Collection>& c1, double w0, double w1) {
+    for (size_t i = 0; i < c0.size(); ++i) {
+      Points<float>& p0 = std::get<Points<float>>(c0[i]);
+      Points<float>& p1 = std::get<Points<float>>(c1[i]);
+      p0.move(time, dt, w0, p0, w1, p1);
+    }
+  };
+  if (ref_derivs(fs, vort, bdry, fldpt, 0, time, solve, user, vs, ss)) return -2;
   if (order == 1) {
-    for (auto& coll : vort) std::visit([=](auto& elem) { elem.move(time, dt, 1.0, elem); }, coll);
+    move_all(vort, dt); move_all(fldpt, dt);
     clear_inner_layer<float>(1, bdry, vort, cutoff, ips);
+    clear_inner_layer<float>(1, bdry, fldpt, cutoff, ips);
   } else if (order == 2) {
     const double twothirds = 2.0/3.0;
     std::vector<Collection> interim = vort;
-    for (auto& coll : interim) std::visit([=](auto& elem) { elem.move(time, twothirds*dt, 1.0, elem); }, coll);
+    move_all(interim, twothirds*dt);
     clear_inner_layer<float>(1, bdry, interim, cutoff, ips);
-    if (ref_derivs(fs, interim, bdry, 1, time + twothirds*dt, solve, user, vs, ss)) return -2;
-    Points<float>& p1 = std::get<Points<float>>(vort[0]);
-    Points<float>& p2 = std::get<Points<float>>(interim[0]);
-    p1.move(time, dt, 0.25, p1, 0.75, p2);
+    std::vector<Collection> interim_f = fldpt;
+    move_all(interim_f, twothirds*dt);
+    clear_inner_layer<float>(1, bdry, interim_f, cutoff, ips);
+    if (ref_derivs(fs, interim, bdry, interim_f, 1, time + twothirds*dt, solve, user, vs, ss)) return -2;
+    move2(vort, interim, 0.25, 0.75);
+    move2(fldpt, interim_f, 0.25, 0.75);
     clear_inner_layer<float>(1, bdry, vort, cutoff, ips);
+    clear_inner_layer<float>(1, bdry, fldpt, cutoff, ips);
   } else {
-    std::vector<Collection> vort1 = vort;
-    for (auto& coll : vort1) std::visit([=](auto& elem) { elem.move(time, 0.5*dt, 1.0, elem); }, coll);
+    std::vector<Collection> vort1 = vort, fld1 = fldpt;
+    move_all(vort1, 0.5*dt);
     clear_inner_layer<float>(1, bdry, vort1, cutoff, ips);
-    if (ref_derivs(fs, vort1, bdry, 1, time + 0.5*dt, solve, user, vs, ss)) return -2;
-    std::vector<Collection> vort2 = vort;
-    {
-      Points<float>& p1 = std::get<Points<float>>(vort1[0]);
-      Points<float>& p2 = std::get<Points<float>>(vort2[0]);
-      p2.move(time, 0.75*dt, 1.0, p1);
-    }
+    move_all(fld1, 0.5*dt);
+    clear_inner_layer<float>(1, bdry, fld1, cutoff, ips);
+    if (ref_derivs(fs, vort1, bdry, fld1, 1, time + 0.5*dt, solve, user, vs, ss)) return -2;
+    std::vector<Collection> vort2 = vort, fld2 = fldpt;
+    for (size_t i = 0; i < vort.size(); ++i)
+      std::get<Points<float>>(vort2[i]).move(time, 0.75*dt, 1.0, std::get<Points<float>>(vort1[i]));
     clear_inner_layer<float>(1, bdry, vort2, cutoff, ips);
-    if (ref_derivs(fs, vort2, bdry, 2, time + 0.75*dt, solve, user, vs, ss)) return -2;
-    Points<float>& p0 = std::get<Points<float>>(vort[0]);
-    Points<float>& p1 = std::get<Points<float>>(vort1[0]);
-    Points<float>& p2 = std::get<Points<float>>(vort2[0]);
-    p0.move(time, dt, 2.0/9.0, p0, 3.0/9.0, p1, 4.0/9.0, p2);
+    for (size_t i = 0; i < fldpt.size(); ++i)
+      std::get<Points<float>>(fld2[i]).move(time, 0.75*dt, 1.0, std::get<Points<float>>(fld1[i]));
+    clear_inner_layer<float>(1, bdry, fld2, cutoff, ips);
+    if (ref_derivs(fs, vort2, bdry, fld2, 2, time + 0.75*dt, solve, user, vs, ss)) return -2;
+    for (size_t i = 0; i < vort.size(); ++i) {
+      Points<float>& p0 = std::get<Points<float>>(vort[i]);
+      p0.move(time, dt, 2.0/9.0, p0, 3.0/9.0, std::get<Points<float>>(vort1[i]), 4.0/9.0, std::get<Points<float>>(vort2[i]));
+    }
+    for (size_t i = 0; i < fldpt.size(); ++i) {
+      Points<float>& p0 = std::get<Points<float>>(fldpt[i]);
+      p0.move(time, dt, 2.0/9.0, p0, 3.0/9.0, std::get<Points<float>>(fld1[i]), 4.0/9.0, std::get<Points<float>>(fld2[i]));
+    }
     clear_inner_layer<float>(1, bdry, vort, cutoff, ips);
+    clear_inner_layer<float>(1, bdry, fldpt, cutoff, ips);
   }
   get_xu(vort[0], n, x, y, u, v);
+  if (nf > 0) get_xu(fldpt[0], nf, fx, fy, fu, fv);
   return 0;
 }
 

@@ -52,7 +52,8 @@ int o2dref_affect_bricks(int from_panels, int results,
 typedef int (*bem_solve_fn)(void* user, int stage, double time, int np, const float* pu, const float* pv, float* vs, float* ss);
 int o2dref_advect_bodies(int order, int n, float* x, float* y, const float* s, const float* r, float* u, float* v,
                          int np, int nnodes, const float* nx, const float* ny, const uint32_t* idx, float* vs, float* ss,
-                         double fsx, double fsy, double time, double dt, float ips, bem_solve_fn solve, void* user);
+                         double fsx, double fsy, double time, double dt, float ips,
+                         int nf, float* fx, float* fy, float* fu, float* fv, bem_solve_fn solve, void* user);
 }
 
 // stand-in for the application's BEM solve (Eigen is not in this image): sheet strengths that cancel the tangential and
@@ -253,10 +254,25 @@ int main() {
       for (size_t i = 0; i < nv; ++i) { qx[i] = 0.92f * vx[i]; qy[i] = 0.92f * vy[i]; pq[2*i] = qx[i]; pq[2*i+1] = qy[i]; }
       Points<float> pts(ElementPacket<float>(pq, std::vector<Int>(), vs, nv, 0), active, lagrangian, nullptr, vdelta);
       Surfaces<float> surf = std::get<Surfaces<float>>(bdry[0]);
-      advect_with_body<float>(order, 0.0, dt, fs, ips, pts, surf, bemfn);
-      std::vector<float> wu(nv), wv(nv), ws(pvs), wss(pss);
+      // tracers close to the body ride along (inert Lagrangian Points, like the reference's fldpt collections)
+      std::vector<float> tfx(nf), tfy(nf), ptf(2 * nf);
+      for (size_t i = 0; i < nf; ++i) { tfx[i] = 0.45f * fx[i]; tfy[i] = 0.45f * fy[i] - 0.1f; ptf[2*i] = tfx[i]; ptf[2*i+1] = tfy[i]; }
+      Points<float> trc(ElementPacket<float>(ptf, std::vector<Int>(), std::vector<float>(), nf, 0), inert, lagrangian, nullptr, 0.0f);
+      advect_with_body<float>(order, 0.0, dt, fs, ips, pts, surf, bemfn, &trc);
+      std::vector<float> wu(nv), wv(nv), ws(pvs), wss(pss), tfu(nf), tfv(nf);
       o2dref_advect_bodies(order, (int)nv, qx.data(), qy.data(), vs.data(), vr.data(), wu.data(), wv.data(), (int)np, (int)np,
-                           nx.data(), ny.data(), idx.data(), ws.data(), wss.data(), fs[0], fs[1], 0.0, dt, ips, &SyntheticBem::c_call, &bemfn);
+                           nx.data(), ny.data(), idx.data(), ws.data(), wss.data(), fs[0], fs[1], 0.0, dt, ips,
+                           (int)nf, tfx.data(), tfy.data(), tfu.data(), tfv.data(), &SyntheticBem::c_call, &bemfn);
+      {
+        double dtr = 0.0;
+        for (size_t i = 0; i < nf; ++i)
+          dtr = std::max(dtr, std::hypot((double)trc.get_pos()[0][i] - tfx[i], (double)trc.get_pos()[1][i] - tfy[i]));
+        char w2[96];
+        std::snprintf(w2, sizeof(w2), "advect_with_body order %d: tracer velocities", order);
+        check(w2, rel_err(trc.get_vel()[0], trc.get_vel()[1], tfu, tfv), 1e-5);
+        std::snprintf(w2, sizeof(w2), "advect_with_body order %d: tracer max |dx|", order);
+        check(w2, dtr, 0.0011 * ips + 2e-6);
+      }
       double d = 0.0; size_t flips = 0;
       for (size_t i = 0; i < nv; ++i) {
         const double di = std::hypot((double)pts.get_pos()[0][i] - qx[i], (double)pts.get_pos()[1][i] - qy[i]);

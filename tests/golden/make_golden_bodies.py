@@ -41,16 +41,22 @@ def main():
     ttx, tty, tnx, tny, area = oracle.port().panel_bases(nx, ny, idx)
     # particles from just inside the surface (they get pushed out) to one radius away
     x, y, s, r = W.annulus_blobs(3000, rin=0.495, rout=1.0, seed=17)
-    out.update(nx=nx, ny=ny, idx=idx, ttx=ttx, tty=tty, tnx=tnx, tny=tny, area=area, x=x, y=y, s=s, r=r,
+    # inert Lagrangian field points (tracers) around the body, some inside the clear layer: they ride along in every stage
+    fx, fy, _, _ = W.annulus_blobs(400, rin=0.497, rout=0.8, seed=23)
+    out.update(nx=nx, ny=ny, idx=idx, ttx=ttx, tty=tty, tnx=tnx, tny=tny, area=area, x=x, y=y, s=s, r=r, fx=fx, fy=fy,
                ips=np.array([IPS]), dt=np.array([DT]), fs=np.array(FS))
     solve = synthetic_solve(ttx, tty, tnx, tny)
     zeros = np.zeros(143, np.float32)
     for core in ("v2", "rm"):
         R = oracle.ref(core)
         for order in (1, 2, 3):
-            res = R.advect_bodies(order, x, y, s, r, (nx, ny, idx, zeros, zeros), solve, DT, float(IPS), FS, time=0.0)
+            res = R.advect_bodies(order, x, y, s, r, (nx, ny, idx, zeros, zeros), solve, DT, float(IPS), FS, time=0.0, fldpt=(fx, fy))
             out[f"{core}_o{order}"] = np.stack(res[:4])
             out[f"{core}_o{order}_str"] = np.stack(res[4:6])
+            out[f"{core}_o{order}_fld"] = np.stack(res[6:10])
+            # the particles must not depend on whether tracers ride along
+            alone = R.advect_bodies(order, x, y, s, r, (nx, ny, idx, zeros, zeros), solve, DT, float(IPS), FS, time=0.0)
+            assert all(np.array_equal(a, b) for a, b in zip(alone[:6], res[:6]))
             moved = np.hypot(res[0] - x, res[1] - y)
             print(core, order, "max displacement", moved.max(), "vs", float(np.abs(res[4]).max()))
     path = os.path.join(ROOT, "tests", "golden", "ref_golden_bodies.npz")

@@ -34,8 +34,9 @@ def test_advect_bodies_golden(core, order, ctx, gb):
         return inner(stage, time, pu, pv)
     z = np.zeros(143, np.float32)
     ips, dt, fs = float(g["ips"][0]), float(g["dt"][0]), tuple(g["fs"])
-    x, y, u, v, vs, ss = ctx.advect_bodies_np(core, order, g["x"], g["y"], g["s"], g["r"], (g["nx"], g["ny"], g["idx"], z, z),
-                                              g["area"], (g["tnx"], g["tny"]), solve, dt, ips, fs)
+    x, y, u, v, vs, ss, fx, fy, fu, fv = ctx.advect_bodies_np(core, order, g["x"], g["y"], g["s"], g["r"],
+                                                              (g["nx"], g["ny"], g["idx"], z, z), g["area"], (g["tnx"], g["tny"]),
+                                                              solve, dt, ips, fs, fldpt=(g["fx"], g["fy"]))
     want = g[f"{core}_o{order}"]
     # one solve per stage, at the reference's stage times
     frac = {1: [0.0], 2: [0.0, 2.0 / 3.0], 3: [0.0, 0.5, 0.75]}[order]
@@ -55,6 +56,16 @@ def test_advect_bodies_golden(core, order, ctx, gb):
     cutoff = 0.5 / np.sqrt(2.0 * np.pi)
     assert (np.hypot(x, y) > apo + (cutoff - 0.0011) * ips - 1e-6).all()
     assert (np.hypot(g["x"], g["y"]) < apo + (cutoff - 0.0011) * ips).sum() > 20     # the input had particles in it
+    # the inert field points that rode along: same checks against the reference's tracers
+    wf = g[f"{core}_o{order}_fld"]
+    assert W.rel_err((fu, fv), (wf[2], wf[3])) < 1e-5
+    df = np.hypot(fx - wf[0], fy - wf[1])
+    assert (df > 2e-6).mean() <= 5e-3 and df.max() <= 0.0011 * ips + 2e-6, (df.max(), (df > 2e-6).sum())
+    assert (np.hypot(fx, fy) > apo + (cutoff - 0.0011) * ips - 1e-6).all()
+    # ... and without them the particles come out bit-identical
+    alone = ctx.advect_bodies_np(core, order, g["x"], g["y"], g["s"], g["r"], (g["nx"], g["ny"], g["idx"], z, z), g["area"],
+                                 (g["tnx"], g["tny"]), inner, dt, ips, fs)
+    assert np.array_equal(alone[0], x) and np.array_equal(alone[1], y) and np.array_equal(alone[2], u)
 
 
 def test_advect_bodies_argument_errors(ctx, gb):
