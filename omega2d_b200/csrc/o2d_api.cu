@@ -512,7 +512,7 @@ extern "C" int o2d_points_vorticity(o2d_context* c, int mem,
 static int panels_run_packed(o2d_context* c, int np_padded, int nt, const float* tx, const float* ty, float* tu, float* tv) {
   const int ntiles = np_padded / kPanelTile;
   // two targets per thread halve the shared-memory reads per pair; one per thread when that would leave SMs idle
-  const int rpt = (nt >= 2 * 256 * c->sm_count * panels_occupancy(2) || (nt >= 256 * c->sm_count && ntiles >= 8)) ? 2 : 1;
+  const int rpt = (nt >= kPanBigR * 256 * c->sm_count * panels_occupancy(kPanBigR) || (nt >= 128 * kPanBigR * c->sm_count && ntiles >= 8)) ? kPanBigR : 1;
   const int nb = (nt + 128 * rpt - 1) / (128 * rpt);
   const int slots = c->sm_count * panels_occupancy(rpt);
   const int nchunks = choose_chunks(nb, ntiles, slots, 256);
@@ -549,18 +549,18 @@ int o2d_panels_multi_device(o2d_context* c, int npan, const o2d_panels_view* pan
   if (last < 0 || nt <= 0) return O2D_OK;
   const long long np_padded = (total + kPanelTile - 1) / kPanelTile * kPanelTile;
   if (np_padded > INT_MAX) return fail(O2D_ERR_INVALID, "more than 2^31 panels in one evaluation");
-  CU(c->panel_packed.reserve((size_t)np_padded * 32));
-  float4* packed = c->panel_packed.as<float4>();   // 4 float4 per panel PAIR = 2 per panel
+  CU(c->panel_packed.reserve((size_t)np_padded * (16 * kPanelRecF4)));
+  float4* packed = c->panel_packed.as<float4>();   // kPanelRecF4 float4 per panel
   long long off = 0;
   for (int k = 0; k < npan; ++k) {
     if (pan[k].np <= 0) continue;
     const int even = (pan[k].np + 1) / 2 * 2;
-    CU(launch_pack_panels(pan[k].np, pan[k].nx, pan[k].ny, pan[k].idx, pan[k].vs, pan[k].ss, packed + 2 * off, even, c->stream));
+    CU(launch_pack_panels(pan[k].np, pan[k].nx, pan[k].ny, pan[k].idx, pan[k].vs, pan[k].ss, packed + kPanelRecF4 * off, even, c->stream));
     c->launches++;
     off += even;
   }
   if (np_padded > off) {
-    CU(launch_pack_panels(pan[last].np, pan[last].nx, pan[last].ny, pan[last].idx, pan[last].vs, pan[last].ss, packed + 2 * off,
+    CU(launch_pack_panels(pan[last].np, pan[last].nx, pan[last].ny, pan[last].idx, pan[last].vs, pan[last].ss, packed + kPanelRecF4 * off,
                           (int)(np_padded - off), c->stream, pan[last].np));
     c->launches++;
   }
@@ -572,7 +572,7 @@ int o2d_panels_on_points_device(o2d_context* c, int np, const float* nx, const f
                                    float* tu, float* tv) {
   if (np <= 0 || nt <= 0) return O2D_OK;
   const int np_padded = (np + kPanelTile - 1) / kPanelTile * kPanelTile;
-  CU(c->panel_packed.reserve((size_t)np_padded * 32));
+  CU(c->panel_packed.reserve((size_t)np_padded * (16 * kPanelRecF4)));
   CU(launch_pack_panels(np, nx, ny, idx, vs, ss, c->panel_packed.as<float4>(), np_padded, c->stream));
   c->launches++;
   return panels_run_packed(c, np_padded, nt, tx, ty, tu, tv);

@@ -89,7 +89,7 @@ __device__ __forceinline__ float atan2_fast(float c, float d) {
 // ustar, vstar of one (panel, point) pair.  vstar = 0.5 log(rij2/rij12) = atanh(z) with
 // z = (rij2 - rij12)/(rij2 + rij12): the numerator is formed without cancellation from the panel
 // vector, and for |z| < 0.2 (point further than ~2.5 panel lengths away: almost every pair) the odd
-// series z + z^3/3 + ... + z^9/9 is exact to 6e-8 relative.  Closer in, two MUFU.LG2 are accurate
+// series z + z^3/3 + ... + z^9/9 is exact to 6e-8 relative.  Closer in, one MUFU.LG2 of the ratio is accurate
 // enough in relative terms because |vstar| >= 0.2; that path is skipped warp-wide when no lane needs it.
 __device__ __forceinline__ void panel_pair(float x0, float y0, float px, float py, float tx, float ty,
                                            float& ustar, float& vstar) {
@@ -102,6 +102,9 @@ __device__ __forceinline__ void panel_pair(float x0, float y0, float px, float p
   const float cross = fmaf(py, dx0, -(px * dy0));
   const float dot = fmaf(dx0, dx1, dy0 * dy1);
   ustar = atan2_fast(cross, dot);
+  // a target exactly ON the panel, between its nodes: the angle is +-pi and the reference's difference of two atan2
+  // (src/Kernels.h:262-268, arguments (dx, dy)) lands on -pi when the panel points to +x (or straight down), +pi otherwise
+  if (cross == 0.0f && dot < 0.0f) ustar = (px > 0.0f || (px == 0.0f && py < 0.0f)) ? -3.14159265358979f : 3.14159265358979f;
   const float num = fmaf(px, dx0 + dx1, py * (dy0 + dy1));   // = rij2 - rij12
   const float z = num * mufu_rcp(rij2 + rij12);
   const float w = z * z;
@@ -111,7 +114,9 @@ __device__ __forceinline__ void panel_pair(float x0, float y0, float px, float p
   vstar = fmaf(z * w, q, z);
   const bool near = !(fabsf(z) < 0.2f);          // also catches NaN (point on a node)
   if (__any_sync(__activemask(), near)) {
-    const float lg = 0.34657359027997264f * (mufu_lg2(rij2) - mufu_lg2(rij12));   // 0.5 ln 2
+    // 0.5 ln 2 * lg2 of the RATIO: the difference of two lg2 of small squared distances (lg2 ~ -17 for millimetre panels)
+    // would carry the absolute rounding of each, 1.6e-6 of vstar at |z| = 0.2
+    const float lg = 0.34657359027997264f * mufu_lg2(rij2 * mufu_rcp(rij12));
     vstar = near ? lg : vstar;
   }
 }
@@ -152,36 +157,46 @@ __device__ __forceinline__ void panel_far2(float2 ex, float2 ey, float2 Hx, floa
   ri = fma2(zx, qi, mul2(zy, qr));
 }
 
-// The same with the series length chosen per warp: beyond |zeta|^2 < kVeryFarZeta2 (targets further than ~6 panel lengths
-// from the panel centre: nearly every pair of a body seen from the flow) the w^3/7 term is below 4.3e-8 relative too and is
-// dropped -- 22 instead of 26 lane-ops.  thr2 = |H|^2 / kVeryFarZeta2 per lane; the choice is one warp vote, so the
-// branch is uniform.  Lanes that fail even kFarZeta2 are the caller's business, as with panel_far2.
+// ---- far field as a Laurent series with per-panel coefficients (round 2) -----------------------------------
+// The strengths and the rotation by the panel tangent are linear, and H is a per-panel constant, so everything but
+// 1/e folds into coefficients:  with g = conj(1/e) = e/|e|^2 and G = g^2
+//   conj(atanh(H/e)) = g (E1 + E3 G + E5 G^2 + E7 G^3),   E_k = conj(H)^k / k ,
+// and for panels acting on a point  u + i v += g (D1 + D3 G + D5 G^2 + D7 G^3),  D_k = m E_k  with m = i (a + i b) the
+// strength-weighted tangent (pack_panels_kernel) -- no per-pair zeta, no per-pair rotation: e (4 lane-ops, the exact
+// (t - node0) + H), |e|^2 (2), g (2), G (4), one complex Horner level (4) per term after the first, and the product with g
+// accumulated by four FMAs: 20 / 24 / 28 lane-ops + one MUFU.RCP for 2 / 3 / 4 terms (round 1's zeta form: 34 for 4).
+// Series length per warp vote, relative truncation error <= 4.3e-8 in each tier:
+//   |zeta|^2 < kFarZeta2 (3.2 panel lengths)   4 terms     next term |zeta|^8/9
+//   |zeta|^2 < kVeryFarZeta2 (6.2 lengths)     3 terms     |zeta|^6/7
+//   |zeta|^2 < kUltraFarZeta2 (23 lengths)     2 terms     |zeta|^4/5
 constexpr float kVeryFarZeta2 = 0.0066f;
-__device__ __forceinline__ void panel_far2v(float2 ex, float2 ey, float2 Hx, float2 Hy, float2 thr2,
-                                            float2& rr, float2& ri, float2& e2) {
+constexpr float kUltraFarZeta2 = 0.00046f;
+
+__device__ __forceinline__ void panel_far_g(float2 ex, float2 ey, float2& gx, float2& gy, float2& Gx, float2& Gy, float2& e2) {
   e2 = fma2(ex, ex, mul2(ey, ey));
   const float2 r = rcp2(e2);
-  const float2 qx = mul2(ex, r), qy = mul2(ey, r);
-  const float2 zx = fma2(Hx, qx, mul2(Hy, qy));            // zeta' = H conj(e) / |e|^2
-  const float2 zy = fma2(Hy, qx, neg2(mul2(Hx, qy)));
-  const float2 wx = fma2(zx, zx, neg2(mul2(zy, zy)));      // w = zeta'^2
-  const float2 wy = mul2(add2(zx, zx), zy);
-  float2 qr, qi;
-  if (__all_sync(0xffffffffu, e2.x > thr2.x && e2.y > thr2.y)) {
-    const float2 tr = fma2(f2(0.2f), wx, f2(1.0f / 3.0f));  // 1/3 + w/5
-    const float2 ti = mul2(f2(0.2f), wy);
-    qr = fma2(tr, wx, fma2(neg2(ti), wy, f2(1.0f)));
-    qi = fma2(tr, wy, mul2(ti, wx));
-  } else {
-    float2 ar = fma2(f2(1.0f / 7.0f), wx, f2(0.2f));       // Horner in the complex w
-    float2 ai = mul2(f2(1.0f / 7.0f), wy);
-    const float2 tr = fma2(ar, wx, fma2(neg2(ai), wy, f2(1.0f / 3.0f)));
-    const float2 ti = fma2(ar, wy, mul2(ai, wx));
-    qr = fma2(tr, wx, fma2(neg2(ti), wy, f2(1.0f)));
-    qi = fma2(tr, wy, mul2(ti, wx));
+  gx = mul2(ex, r); gy = mul2(ey, r);
+  Gx = fma2(gx, gx, neg2(mul2(gy, gy)));
+  Gy = mul2(add2(gx, gx), gy);
+}
+// one Horner level in the complex G:  t <- t G + D
+__device__ __forceinline__ void chorner(float2& tr, float2& ti, float2 Gx, float2 Gy, float2 Dx, float2 Dy) {
+  const float2 nr = fma2(tr, Gx, fma2(neg2(ti), Gy, Dx));
+  const float2 ni = fma2(tr, Gy, fma2(ti, Gx, Dy));
+  tr = nr; ti = ni;
+}
+// E_k = conj(H)^k / k, k = 1,3,5,7, times the complex m, in float64 (pack time / once per thread)
+__device__ __forceinline__ void panel_far_coeffs(double hx, double hy, double mx, double my, float* dx, float* dy) {
+  const double cx = hx, cy = -hy;                        // conj(H)
+  const double c2x = cx * cx - cy * cy, c2y = 2.0 * cx * cy;
+  double px = mx * cx - my * cy, py = mx * cy + my * cx; // m conj(H)^k
+  const double inv[4] = {1.0, 1.0 / 3.0, 0.2, 1.0 / 7.0};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    dx[k] = (float)(px * inv[k]); dy[k] = (float)(py * inv[k]);
+    const double qx = px * c2x - py * c2y, qy = px * c2y + py * c2x;
+    px = qx; py = qy;
   }
-  rr = fma2(zx, qr, neg2(mul2(zy, qi)));
-  ri = fma2(zx, qi, mul2(zy, qr));
 }
 
 // ---- radius terms ----------------------------------------------------------------------------

@@ -46,7 +46,7 @@ struct PPArgs {
 };
 
 struct PanelArgs {
-  const float4* packed;   // 4 float4 per panel PAIR (layout: pack_panels_kernel)
+  const float4* packed;   // kPanelRecF4 float4 per panel, 2*kPanelRecF4 per panel PAIR (layout: pack_panels_kernel)
   int npanels_padded;     // multiple of kPanelTile
   int tiles_per_chunk;
   const float* tx;
@@ -57,6 +57,11 @@ struct PanelArgs {
 };
 
 constexpr int kPanelTile = 256;  // panels (or particles, for points-on-panels) per smem tile
+#ifndef O2D_PAN_BIG_R
+#define O2D_PAN_BIG_R 2
+#endif
+constexpr int kPanBigR = O2D_PAN_BIG_R;   // targets per thread of the panels-on-points kernel when there are enough targets
+constexpr int kPanelRecF4 = 4;   // float4 per packed panel (16 floats: node0, H, four complex series coefficients, thresholds)
 
 // number of raw accumulated components per result kind (mirrors ResTraits in o2d_pp_impl.cuh)
 inline int res_ncomp(int res) {
@@ -125,7 +130,7 @@ cudaError_t launch_pack_sources(int mode, int ns, const float* sx, const float* 
 cudaError_t launch_pack_panels(int np, const float* nx, const float* ny, const uint32_t* idx,
                                const float* vs, const float* ss, float4* packed, int np_padded,
                                cudaStream_t st, int j0 = 0);
-// rpt: targets per thread (1 or 2); grid.x covers 128*rpt targets per CTA
+// rpt: targets per thread (1 or kPanBigR); grid.x covers 128*rpt targets per CTA
 cudaError_t launch_panels_on_points(const PanelArgs& a, int nchunks, int rpt, cudaStream_t st);
 cudaError_t launch_panels_combine(const double* partial, int nchunks, int nt, const OutPtrs& out, cudaStream_t st);
 // points-on-panels: targets are panels (one per thread), sources are packed particles

@@ -169,6 +169,48 @@ def test_panels_random_strengths_noise_floor(ctx, port):
     _panel_check(got, want, panels_on_points_f64(nx, ny, idx, vs, ss, x, y))
 
 
+@pytest.mark.parametrize("angle", [0.0, 0.7, 2.3])
+def test_panel_series_tiers_per_target(angle, ctx):
+    """The far field is a Laurent series cut after 2, 3 or 4 terms by distance (23 / 6.2 / 3.2 panel lengths, per warp
+    vote), the near field the general form.  Targets on rays from 0.05 to 3000 panel lengths from ONE short panel far
+    from the origin, shuffled so warps mix tiers: every target within 1e-6 of float64 RELATIVE TO ITS OWN value (the
+    reference's own float32 form is off by up to 4e-4 here, src/Kernels.h:312-405)."""
+    from oracle.f64 import panels_on_points_f64, points_on_panels_f64
+    L = 1.0e-3
+    c = np.array([1.25, -0.75])
+    d = 0.5 * L * np.array([np.cos(angle), np.sin(angle)])
+    nx = np.array([c[0] - d[0], c[0] + d[0]], np.float32); ny = np.array([c[1] - d[1], c[1] + d[1]], np.float32)
+    idx = np.array([0, 1], np.uint32)
+    vs = np.array([0.8], np.float32); ss = np.array([-0.6], np.float32)
+    rng = np.random.default_rng(5)
+    dist = L * np.logspace(np.log10(0.05), np.log10(3000.0), 6000)
+    th = rng.uniform(0, 2 * np.pi, dist.size)
+    x = (c[0] + dist * np.cos(th)).astype(np.float32); y = (c[1] + dist * np.sin(th)).astype(np.float32)
+    for order in (np.arange(dist.size), rng.permutation(dist.size)):     # sorted: uniform warps; shuffled: mixed warps
+        xs, ys = x[order], y[order]
+        got = ctx.panels_on_points_np(nx, ny, idx, vs, ss, xs, ys)
+        exact = panels_on_points_f64(nx, ny, idx, vs, ss, xs, ys)
+        mag = np.hypot(exact[0], exact[1])
+        err = np.hypot(got[0] - exact[0], got[1] - exact[1]) / mag
+        assert err.max() < 1e-6, (err.max(), dist[order][err.argmax()] / L)
+    # targets exactly ON the panel between its nodes (ustar = +-pi): the side the reference's two-atan2 form picks
+    if angle == 0.0:
+        for sgn in (1.0, -1.0):
+            nxs = (nx if sgn > 0 else nx[::-1]).copy()
+            xs = np.array([c[0] + 0.2 * L, c[0] - 0.3 * L], np.float32); ys = np.array([ny[0], ny[0]], np.float32)
+            got = ctx.panels_on_points_np(nxs, ny, idx, vs, ss, xs, ys)
+            exact = panels_on_points_f64(nxs, ny, idx, vs, ss, xs, ys)
+            assert W.rel_err(got, exact) < 1e-6, (sgn, got, exact)
+    # the reciprocal kernel: unit-strength particles, one at a time, on the panel
+    area = np.array([L], np.float32)
+    for k in range(0, dist.size, 97):
+        one = np.array([1.0], np.float32)
+        got = ctx.points_on_panels_np(x[k:k + 1], y[k:k + 1], one, nx, ny, idx, area)
+        exact = points_on_panels_f64(x[k:k + 1], y[k:k + 1], one, nx, ny, idx, area)
+        mag = float(np.hypot(exact[0][0], exact[1][0]))
+        assert float(np.hypot(got[0][0] - exact[0][0], got[1][0] - exact[1][0])) / mag < 1e-6, (k, dist[k] / L)
+
+
 def test_closed_ring_property(ctx):
     nx, ny, idx, vs, _ = W.circle_panels(2000, radius=0.5)
     vs[:] = 1.0
