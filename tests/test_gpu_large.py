@@ -140,3 +140,29 @@ def test_2m_particles_wl_and_v2(core, ctx, large):
     assert err < TOL, err
     gsum = abs(np.dot(arrs[2].astype(np.float64), u.astype(np.float64))) / (np.abs(arrs[2]).sum() * scale)
     assert gsum < 1e-5
+
+
+def test_c5_16m_wl_sources(ctx):
+    """BASELINE configs[4] (C5): ALL 16 777 216 Winckelmans-Leonard particles as sources -- the accumulation length the
+    strong/weak sweeps of profiles/r02_multi_gpu.md run at -- summed onto 65 536 strided targets (1.1e12 pairs); 256 of
+    them against the reference's own points_affect_points (tests/golden/make_golden_c5.py)."""
+    import os, torch
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_golden_c5.npz"))
+    n = 16_777_216
+    arrs = W.gaussian_blob(n, seed=2024)
+    _check_inputs(arrs, gold["c5_input_checksum"])
+    tsub, csub = gold["c5_targets"], gold["c5_check"]
+    np.testing.assert_array_equal(arrs[0][tsub[csub]], gold["c5_tx"])
+    dev = torch.device("cuda:0")
+    d = [torch.from_numpy(a).to(dev) for a in arrs]
+    it = torch.from_numpy(tsub).to(dev)
+    tx, ty, tr = d[0][it].contiguous(), d[1][it].contiguous(), d[3][it].contiguous()
+    nt = tsub.size
+    tu = torch.zeros(nt, device=dev); tv = torch.zeros(nt, device=dev)
+    ctx.points_on_points("wl", o2d.VELONLY, o2d.MEM_DEVICE, n, d[0], d[1], d[2], d[3], nt, tx, ty, tr, tu, tv)
+    ctx.synchronize()
+    u, v = tu.cpu().numpy(), tv.cpu().numpy()
+    ref = gold["c5_wl"]
+    scale = np.sqrt(u.astype(np.float64) ** 2 + v.astype(np.float64) ** 2).max()
+    err = np.sqrt((u[csub] - ref[0]).astype(np.float64) ** 2 + (v[csub] - ref[1]).astype(np.float64) ** 2).max() / scale
+    assert err < TOL, err
