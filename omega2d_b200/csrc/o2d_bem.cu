@@ -16,9 +16,8 @@
 //
 // Mapping: one thread per target panel (rows are contiguous in memory -> coalesced 8-byte stores),
 // source panels staged 64 at a time in shared memory and broadcast.  Each pair costs two panel_pair()
-// evaluations (FMA-pipe atan2/atanh, see o2d_device.cuh) and writes 16 (or 4) bytes: for Np = 20k that is
-// 4e8 pairs, 6.4 GB of coefficients -- the store stream and the ~130 instructions per pair are of
-// the same order, so the kernel is neither purely HBM- nor FP32-bound.
+// evaluations (the Laurent far-field series of o2d_device.cuh, two terms for nearly every pair; panel_pair() close in)
+// and writes 16 (or 4) bytes: for Np = 20k that is 4e8 pairs, 6.4 GB of coefficients -- the store stream is the bound.
 #include "o2d_context.h"
 #include "o2d_device.cuh"
 
@@ -29,10 +28,12 @@ namespace {
 constexpr int kCoefThreads = 128;
 constexpr int kCoefSrcTile = 64;
 
-// per panel: {x0, y0, Hx, Hy} {cx, cy, area, thr} {Ux, Uy, -, -}
-//   H = -p/2 and thr = |H|^2/kFarZeta2 feed panel_far2 (o2d_device.cuh); U = -2 p/|p| is the unit tangent in
-//   panel_far2's output scaling (it returns -ustar/2, -vstar/2)
-constexpr int kCoefRec = 3;
+// per panel: {x0, y0, Hx, Hy} {cx, cy, area, thr} {D1x, D1y, D3x, D3y} {D5x, D5y, D7x, D7y} {Ux, Uy, thr2, thr3}
+//   H = -p/2; thr, thr2, thr3 = |H|^2 / kFarZeta2, / kVeryFarZeta2, / kUltraFarZeta2 (4, 3, 2 series terms; inside thr the
+//   general panel_pair); D_k = m conj(H)^k / k with m = i (Ux + i Uy), U = -2 p/|p|: the Laurent coefficients of the
+//   velocity of this panel carrying UNIT vortex sheet strength (o2d_device.cuh, "far field as a Laurent series"); U itself
+//   is what the near form multiplies its (-ustar/2, -vstar/2) with
+constexpr int kCoefRec = 5;
 __global__ void __launch_bounds__(256)
 pack_coeff_panels_kernel(int np, const float* __restrict__ nx, const float* __restrict__ ny,
                          const uint32_t* __restrict__ idx, const float* __restrict__ area,
@@ -43,11 +44,17 @@ pack_coeff_panels_kernel(int np, const float* __restrict__ nx, const float* __re
   const float x0 = nx[i0], y0 = ny[i0], x1 = nx[i1], y1 = ny[i1];
   const float px = x1 - x0, py = y1 - y0;
   const float hx = -0.5f * px, hy = -0.5f * py;
-  const float rlen = 1.0f / sqrtf(px * px + py * py);
+  const double rlen = 1.0 / sqrt((double)px * px + (double)py * py);
+  const double ux = -2.0 * (px * rlen), uy = -2.0 * (py * rlen);
+  float dx[4], dy[4];
+  panel_far_coeffs(hx, hy, -uy, ux, dx, dy);
+  const float thr = (hx * hx + hy * hy) * (1.0f / kFarZeta2);
   packed[kCoefRec * j] = make_float4(x0, y0, hx, hy);
   // collocation point as the reference forms it: 0.5*(x1+x0) (src/Coefficients.h:327-328,356)
-  packed[kCoefRec * j + 1] = make_float4(0.5f * (x1 + x0), 0.5f * (y1 + y0), area[j], (hx * hx + hy * hy) * (1.0f / kFarZeta2));
-  packed[kCoefRec * j + 2] = make_float4(-2.0f * (px * rlen), -2.0f * (py * rlen), 0.0f, 0.0f);
+  packed[kCoefRec * j + 1] = make_float4(0.5f * (x1 + x0), 0.5f * (y1 + y0), area[j], thr);
+  packed[kCoefRec * j + 2] = make_float4(dx[0], dy[0], dx[1], dy[1]);
+  packed[kCoefRec * j + 3] = make_float4(dx[2], dy[2], dx[3], dy[3]);
+  packed[kCoefRec * j + 4] = make_float4((float)ux, (float)uy, thr * (kFarZeta2 / kVeryFarZeta2), thr * (kFarZeta2 / kUltraFarZeta2));
 }
 
 struct CoefArgs {
@@ -78,7 +85,9 @@ coeff_kernel(const CoefArgs a) {
   const int ii = min(i, a.ntarg - 1);
   const float4 T = a.tpack[kCoefRec * (size_t)ii];
   const float4 Tc = a.tpack[kCoefRec * (size_t)ii + 1];
-  const float4 Tu = a.tpack[kCoefRec * (size_t)ii + 2];
+  const float4 Td = a.tpack[kCoefRec * (size_t)ii + 2];
+  const float4 Te = a.tpack[kCoefRec * (size_t)ii + 3];
+  const float4 Tu = a.tpack[kCoefRec * (size_t)ii + 4];
   const float ttx = a.ttx[ii], tty = a.tty[ii];
   const float2 T1 = f2(ttx, BOTH ? a.tnx[ii] : 0.0f);     // {tangent.x, normal.x}
   const float2 T2 = f2(tty, BOTH ? a.tny[ii] : 0.0f);     // {tangent.y, normal.y}
@@ -90,23 +99,43 @@ coeff_kernel(const CoefArgs a) {
     const int j = j0 + jj;
     const float4 S = s[kCoefRec * jj];
     const float4 Sc = s[kCoefRec * jj + 1];
-    const float4 Su = s[kCoefRec * jj + 2];
+    const float4 Sd = s[kCoefRec * jj + 2];
+    const float4 Su = s[kCoefRec * jj + 4];
     const float2 Hx = f2(S.z, T.z), Hy = f2(S.w, T.w);
     const float2 ex = add2(add2(f2(Tc.x, Sc.x), neg2(f2(S.x, T.x))), Hx);
     const float2 ey = add2(add2(f2(Tc.y, Sc.y), neg2(f2(S.y, T.y))), Hy);
-    float2 rr, ri, e2;
-    panel_far2(ex, ey, Hx, Hy, rr, ri, e2);
-    const bool na = !(e2.x > Sc.w), nb = !(e2.y > Tc.w);
-    if (__any_sync(0xffffffffu, na || nb)) {
-      float us, vs;
-      panel_pair(S.x, S.y, -2.0f * S.z, -2.0f * S.w, Tc.x, Tc.y, us, vs);
-      if (na) { ri.x = -0.5f * us; rr.x = -0.5f * vs; }
-      panel_pair(T.x, T.y, -2.0f * T.z, -2.0f * T.w, Sc.x, Sc.y, us, vs);
-      if (nb) { ri.y = -0.5f * us; rr.y = -0.5f * vs; }
+    float2 gx, gy, Gx, Gy, e2;
+    panel_far_g(ex, ey, gx, gy, Gx, Gy, e2);
+    float2 tr, ti;
+    bool near = false;
+    if (__all_sync(0xffffffffu, e2.x > Su.w && e2.y > Tu.w)) {
+      // both directions beyond 23 panel lengths (nearly every pair of a large body): two terms, no further tests
+      tr = fma2(f2(Sd.z, Td.z), Gx, fma2(neg2(f2(Sd.w, Td.w)), Gy, f2(Sd.x, Td.x)));
+      ti = fma2(f2(Sd.z, Td.z), Gy, fma2(f2(Sd.w, Td.w), Gx, f2(Sd.y, Td.y)));
+    } else {
+      const float4 Se = s[kCoefRec * jj + 3];
+      if (__all_sync(0xffffffffu, e2.x > Su.z && e2.y > Tu.z)) {
+        tr = f2(Se.x, Te.x); ti = f2(Se.y, Te.y);
+      } else {
+        tr = f2(Se.z, Te.z); ti = f2(Se.w, Te.w);
+        chorner(tr, ti, Gx, Gy, f2(Se.x, Te.x), f2(Se.y, Te.y));
+      }
+      chorner(tr, ti, Gx, Gy, f2(Sd.z, Td.z), f2(Sd.w, Td.w));
+      chorner(tr, ti, Gx, Gy, f2(Sd.x, Td.x), f2(Sd.y, Td.y));
+      near = true;
     }
-    const float2 Ux = f2(Su.x, Tu.x), Uy = f2(Su.y, Tu.y);
-    const float2 vu2 = fma2(ri, Ux, neg2(mul2(rr, Uy)));   // {vu, wu}
-    const float2 vv2 = fma2(ri, Uy, mul2(rr, Ux));         // {vv, wv}
+    float2 vu2 = fma2(tr, gx, neg2(mul2(ti, gy)));   // {vu, wu}: velocity of the unit vortex sheet = t g
+    float2 vv2 = fma2(tr, gy, mul2(ti, gx));         // {vv, wv}
+    if (near) {
+      const bool na = !(e2.x > Sc.w), nb = !(e2.y > Tc.w);
+      if (__any_sync(0xffffffffu, na || nb)) {
+        float us, vs;
+        panel_pair(S.x, S.y, -2.0f * S.z, -2.0f * S.w, Tc.x, Tc.y, us, vs);
+        if (na) { vu2.x = -0.5f * (us * Su.x - vs * Su.y); vv2.x = -0.5f * (us * Su.y + vs * Su.x); }
+        panel_pair(T.x, T.y, -2.0f * T.z, -2.0f * T.w, Sc.x, Sc.y, us, vs);
+        if (nb) { vu2.y = -0.5f * (us * Tu.x - vs * Tu.y); vv2.y = -0.5f * (us * Tu.y + vs * Tu.x); }
+      }
+    }
     const float fact = Sc.z * rta;                         // sa[j]/ta[i]
     const bool self = a.same && (i == j);
     if (i >= a.ntarg) continue;
