@@ -127,35 +127,15 @@ __device__ __forceinline__ void panel_pair(float x0, float y0, float px, float p
 // get_ustar's wrapped atan2 difference, src/Kernels.h:262-268; vstar = 0.5 log(rij2/rij12), :338).  With
 // e = t - centre = d0 - p/2 and  zeta = (d0-d1)/(d0+d1) = (p/2)/e:   log(d0/d1) = 2 atanh(zeta)
 //   = 2 zeta (1 + zeta^2/3 + zeta^4/5 + zeta^6/7 + ...),
-// a series in the complex zeta that needs no arctangent, no logarithm and no range reduction: 26 FP32
-// lane-ops + one MUFU.RCP for BOTH outputs (the general panel_pair above is ~55 instructions + 2-4 MUFU), and
-// it has no cancellation (<= 4.5e-7 relative to float64; the reference's own float expression is off by up to
-// 4e-4 relative for short panels).  Truncated after zeta^6/7 the relative error is |zeta|^8/9 <= 4.3e-8 for
-// |zeta|^2 < kFarZeta2, i.e. targets further than 3.16 panel lengths from the panel centre -- all but a
-// handful of pairs; the callers fall back to panel_pair() for the rest (warp-uniform test).
-//   inputs : e = (ex,ey), H = (Hx,Hy) with  H = -p/2  (or e = centre - t and H = +p/2: same zeta' = H conj(e)/|e|^2)
-//   outputs: (rr, ri) with  vstar = -2 rr,  ustar = -2 ri ;  e2 = |e|^2 for the caller's near test
+// a series in the complex zeta that needs no arctangent, no logarithm and no range reduction (the general panel_pair
+// above is ~55 instructions + 2-4 MUFU), and it has no cancellation (<= 4.5e-7 relative to float64; the reference's own
+// float expression is off by up to 4e-4 relative for short panels).  Truncated after zeta^6/7 the relative error is
+// |zeta|^8/9 <= 4.3e-8 for |zeta|^2 < kFarZeta2, i.e. targets further than 3.16 panel lengths from the panel centre --
+// all but a handful of pairs; the callers fall back to panel_pair() for the rest (warp-uniform test).
+// Sign convention kept from round 1's per-pair zeta evaluation: H = -p/2 (or e = centre - t and H = +p/2), so the series
+// gives  (rr, ri) = (-vstar/2, -ustar/2).
 constexpr float kFarZeta2 = 0.025f;
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }   // folds into FFMA2 operand modifiers
-
-__device__ __forceinline__ void panel_far2(float2 ex, float2 ey, float2 Hx, float2 Hy,
-                                           float2& rr, float2& ri, float2& e2) {
-  e2 = fma2(ex, ex, mul2(ey, ey));
-  const float2 r = rcp2(e2);
-  const float2 qx = mul2(ex, r), qy = mul2(ey, r);
-  const float2 zx = fma2(Hx, qx, mul2(Hy, qy));            // zeta' = H conj(e) / |e|^2
-  const float2 zy = fma2(Hy, qx, neg2(mul2(Hx, qy)));
-  const float2 wx = fma2(zx, zx, neg2(mul2(zy, zy)));      // w = zeta'^2
-  const float2 wy = mul2(add2(zx, zx), zy);
-  float2 qr = fma2(f2(1.0f / 7.0f), wx, f2(0.2f));         // Horner in the complex w
-  float2 qi = mul2(f2(1.0f / 7.0f), wy);
-  const float2 tr = fma2(qr, wx, fma2(neg2(qi), wy, f2(1.0f / 3.0f)));
-  const float2 ti = fma2(qr, wy, mul2(qi, wx));
-  qr = fma2(tr, wx, fma2(neg2(ti), wy, f2(1.0f)));
-  qi = fma2(tr, wy, mul2(ti, wx));
-  rr = fma2(zx, qr, neg2(mul2(zy, qi)));
-  ri = fma2(zx, qi, mul2(zy, qr));
-}
 
 // ---- far field as a Laurent series with per-panel coefficients (round 2) -----------------------------------
 // The strengths and the rotation by the panel tangent are linear, and H is a per-panel constant, so everything but

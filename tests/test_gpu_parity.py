@@ -434,7 +434,7 @@ def test_points_status_reductions(n, ctx, port):
 
 def _ring_targets(cx, cy, length, nrho=240, nphi=48, lo=-1.5, hi=2.5):
     """Targets on rings around (cx, cy) at 10**lo .. 10**hi panel lengths: covers the general pair, the far-field
-    series (beyond 3.16 panel lengths, panel_far2 in o2d_device.cuh) and the switch between them."""
+    series (beyond 3.16 panel lengths, panel_far_g / chorner in o2d_device.cuh) and the switch between them."""
     rho = np.logspace(lo, hi, nrho)[:, None] * length
     phi = (np.arange(nphi) + 0.37) * (2 * np.pi / nphi)
     return (cx + rho * np.cos(phi)[None, :]).astype(np.float32).ravel(), (cy + rho * np.sin(phi)[None, :]).astype(np.float32).ravel()
