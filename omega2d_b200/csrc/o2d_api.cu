@@ -509,7 +509,7 @@ extern "C" int o2d_points_vorticity(o2d_context* c, int mem,
 
 // ---- panels ------------------------------------------------------------------------------------------------
 // panels already packed (np_padded of them, a multiple of kPanelTile) onto nt targets
-static int panels_run_packed(o2d_context* c, int np_padded, int nt, const float* tx, const float* ty, float* tu, float* tv) {
+static int panels_run_packed(o2d_context* c, int np_padded, int np_even, int nt, const float* tx, const float* ty, float* tu, float* tv) {
   const int ntiles = np_padded / kPanelTile;
   // two targets per thread halve the shared-memory reads per pair; one per thread when that would leave SMs idle
   const int rpt = (nt >= kPanBigR * 256 * c->sm_count * panels_occupancy(kPanBigR) || (nt >= 128 * kPanBigR * c->sm_count && ntiles >= 8)) ? kPanBigR : 1;
@@ -519,6 +519,7 @@ static int panels_run_packed(o2d_context* c, int np_padded, int nt, const float*
   PanelArgs a;
   a.packed = c->panel_packed.as<float4>();
   a.npanels_padded = np_padded;
+  a.npanels_even = np_even;
   a.tiles_per_chunk = (ntiles + nchunks - 1) / nchunks;
   a.tx = tx; a.ty = ty; a.nt = nt;
   a.out = OutPtrs{};
@@ -564,7 +565,7 @@ int o2d_panels_multi_device(o2d_context* c, int npan, const o2d_panels_view* pan
                           (int)(np_padded - off), c->stream, pan[last].np));
     c->launches++;
   }
-  return panels_run_packed(c, (int)np_padded, nt, tx, ty, tu, tv);
+  return panels_run_packed(c, (int)np_padded, (int)off, nt, tx, ty, tu, tv);
 }
 
 int o2d_panels_on_points_device(o2d_context* c, int np, const float* nx, const float* ny, const uint32_t* idx,
@@ -575,7 +576,7 @@ int o2d_panels_on_points_device(o2d_context* c, int np, const float* nx, const f
   CU(c->panel_packed.reserve((size_t)np_padded * (16 * kPanelRecF4)));
   CU(launch_pack_panels(np, nx, ny, idx, vs, ss, c->panel_packed.as<float4>(), np_padded, c->stream));
   c->launches++;
-  return panels_run_packed(c, np_padded, nt, tx, ty, tu, tv);
+  return panels_run_packed(c, np_padded, (np + 1) / 2 * 2, nt, tx, ty, tu, tv);
 }
 
 extern "C" int o2d_panels_on_points(o2d_context* c, int mem,

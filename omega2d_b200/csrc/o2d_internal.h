@@ -47,7 +47,8 @@ struct PPArgs {
 
 struct PanelArgs {
   const float4* packed;   // kPanelRecF4 float4 per panel, 2*kPanelRecF4 per panel PAIR (layout: pack_panels_kernel)
-  int npanels_padded;     // multiple of kPanelTile
+  int npanels_padded;     // multiple of kPanelTile (what is packed: zero-strength padding behind the real panels)
+  int npanels_even;       // the real panels rounded up to a pair: what the kernel walks (the last tile may be partial)
   int tiles_per_chunk;
   const float* tx;
   const float* ty;

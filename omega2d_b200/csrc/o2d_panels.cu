@@ -122,13 +122,14 @@ panels_on_points_kernel(const PanelArgs a) {
   for (int t = tile_begin; t < tile_end; ++t) {
     __syncthreads();
     const float4* g = a.packed + (size_t)t * (kPanelRecF4 * kPanelTile);
-    for (int k = tid; k < kPanelRecF4 * kPanelTile; k += kPanThreads) s[k] = g[k];
+    const int npairs = min(kPanelTile, a.npanels_even - t * kPanelTile) / 2;   // the last tile may be partial
+    for (int k = tid; k < 2 * kPanelRecF4 * npairs; k += kPanThreads) s[k] = g[k];
     __syncthreads();
     float2 pu[R], pv[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) { pu[k] = f2(0.0f); pv[k] = f2(0.0f); }
 #pragma unroll 2
-    for (int q = 0; q < kPanelTile / 2; ++q) {
+    for (int q = 0; q < npairs; ++q) {
       const float4* rec = s + 8 * q;
       const float4 P = rec[0];        // x0A x0B y0A y0B
       const float4 H = rec[1];        // HxA HxB HyA HyB
@@ -283,6 +284,10 @@ points_on_panels_kernel(const PtPanArgs a) {
     thr2[k] = thr[k] * (kFarZeta2 / kVeryFarZeta2);
     thr3[k] = thr[k] * (kFarZeta2 / kUltraFarZeta2);
   }
+  bool any_ok = false;
+#pragma unroll
+  for (int k = 0; k < kPtPanPPT; ++k) any_ok = any_ok || ok[k];
+  const bool warp_works = __any_sync(0xffffffffu, any_ok);
   const int tile_begin = blockIdx.y * a.tiles_per_chunk;
   const int tile_end = min(tile_begin + a.tiles_per_chunk, a.ntiles);
   double acc1[kPtPanPPT], acc2[kPtPanPPT], M1x[kPtPanPPT], M1y[kPtPanPPT], M3x[kPtPanPPT], M3y[kPtPanPPT];
@@ -300,6 +305,7 @@ points_on_panels_kernel(const PtPanArgs a) {
       pi[k] = f2(0.0f); pr[k] = f2(0.0f);
       m1x[k] = f2(0.0f); m1y[k] = f2(0.0f); m3x[k] = f2(0.0f); m3y[k] = f2(0.0f);
     }
+    if (!warp_works) continue;   // a warp past the last panel only helps staging (143 panels: 3 of the 8 warps)
 #pragma unroll 2
     for (int p = 0; p < kTile / 2; ++p) {
       const float4 A = s[2 * p];      // -x0 -x1 -y0 -y1 of two particles
