@@ -69,30 +69,42 @@ inline int res_ncomp(int res) {
   switch (res) { case 0: return 2; case 1: return 4; case 2: return 3; case 3: return 6; case 4: return 1; }
   return 0;
 }
+#ifndef O2D_UE_R
+#define O2D_UE_R 4
+#endif
+#ifndef O2D_UE_WARPS
+#define O2D_UE_WARPS 16
+#endif
+#ifndef O2D_UE_UNROLL
+#define O2D_UE_UNROLL 4
+#endif
 // ---- pair-sum kernel shape per (core, result kind, configuration) --------------------------------------------
 // targets per thread R, resident warps per SM the register allocation must allow, and inner-loop unroll (source
 // pairs).  Measured on B200, 1M x 1M (pairs/clk/SM; profiles/r02_pp_shape_search.md): RM and V2 velocity are
 // fastest with 16 resident warps of 128 registers and R = 6 (RM 12.89, V2 12.90; 24 warps of 80 registers with
 // R = 4 give 12.56 / 12.56); WL wants R = 4 (10.75 against 10.37), EXP and V3 24 warps and R = 4 (EXP 11.04
 // against 10.33; V3 with uniform radii 7.53 against 6.91); the gradient-type kernels (128 registers, R = 3) lose
-// to any unrolling (RM velocity+gradient 7.23 / 7.22 / 6.98 / 6.84 at 1 / 2 / 8 / 16).
+// to any unrolling (RM velocity+gradient 7.23 / 7.22 / 6.98 / 6.84 at 1 / 2 / 8 / 16); velocity + shear rate: R = 4,
+// 16 warps, unroll 4 (RM 9.56, V2 uniform 9.05; the 24-warp R = 2 shape of the first run-walking version 9.37 / 8.59).
 constexpr int pp_targets(int core, int res, bool fine) {
   if (fine) return (res == RES_U || res == RES_VORT) ? 2 : 1;
   switch (res) {
     case RES_U:    return (core == CORE_WL || core == CORE_EXP || core == CORE_V3) ? 4 : 6;
     case RES_VORT: return 4;
-    case RES_UE:   return 2;
+    case RES_UE:   return O2D_UE_R;
     default:       return 3;   // RES_UW, RES_UG
   }
 }
 constexpr int pp_min_warps(int core, int res, bool fine) {
-  if (res == RES_VORT || res == RES_UE) return 24;
+  if (res == RES_UE) return O2D_UE_WARPS;
+  if (res == RES_VORT) return 24;
   if (res != RES_U) return 16;
   return (fine || core == CORE_EXP || core == CORE_V3) ? 24 : 16;
 }
 constexpr int pp_unroll(int core, int res, bool fine) {
   if (fine || core == CORE_EXP || core == CORE_WL) return 4;
-  if (res == RES_UE || res == RES_VORT) return 8;
+  if (res == RES_UE) return O2D_UE_UNROLL;
+  if (res == RES_VORT) return 8;
   if (res == RES_U) return core == CORE_V3 ? 8 : 16;
   return 1;
 }
