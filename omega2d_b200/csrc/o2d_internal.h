@@ -69,6 +69,12 @@ inline int res_ncomp(int res) {
   switch (res) { case 0: return 2; case 1: return 4; case 2: return 3; case 3: return 6; case 4: return 1; }
   return 0;
 }
+#ifndef O2D_UW_R
+#define O2D_UW_R 3
+#endif
+#ifndef O2D_UW_UNROLL
+#define O2D_UW_UNROLL 1
+#endif
 #ifndef O2D_UE_R
 #define O2D_UE_R 4
 #endif
@@ -92,7 +98,8 @@ constexpr int pp_targets(int core, int res, bool fine) {
     case RES_U:    return (core == CORE_WL || core == CORE_EXP || core == CORE_V3) ? 4 : 6;
     case RES_VORT: return 4;
     case RES_UE:   return O2D_UE_R;
-    default:       return 3;   // RES_UW, RES_UG
+    case RES_UW:   return O2D_UW_R;
+    default:       return 3;   // RES_UG
   }
 }
 constexpr int pp_min_warps(int core, int res, bool fine) {
@@ -105,6 +112,7 @@ constexpr int pp_unroll(int core, int res, bool fine) {
   if (fine || core == CORE_EXP || core == CORE_WL) return 4;
   if (res == RES_UE) return O2D_UE_UNROLL;
   if (res == RES_VORT) return 8;
+  if (res == RES_UW) return O2D_UW_UNROLL;
   if (res == RES_U) return core == CORE_V3 ? 8 : 16;
   return 1;
 }
