@@ -1,5 +1,5 @@
 """Profiling driver: runs ONE operation of the path twice (warm-up + the launch ncu captures) at bench size.
-    python tools/ncu_targets.py pp:rm:2:0 | pp:<core>:<results>:<uniform> | panels | ptpan | cil | reflect   [n] [npanels]"""
+    python tools/ncu_targets.py pp:rm:2:0 | pp:<core>:<results>:<uniform> | panels | ptpan | coeff | cil | reflect   [n] [npanels]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -35,6 +35,18 @@ else:
     elif what == "ptpan":
         pu = torch.zeros(vs.size, device=dev); pv = torch.zeros(vs.size, device=dev)
         fn = lambda: ctx.points_on_panels(o2d.MEM_DEVICE, n, dx, dy, ds, vs.size, nx.size, dp[0], dp[1], dp[2], dp[5], pu, pv)
+    elif what == "coeff":
+        # BEM block of one 20 000-panel circle on itself, both strengths unknown (the panel_bench.py case)
+        cnx, cny, cidx, _, _ = W.circle_panels(npan, radius=0.5)
+        i0, i1 = cidx[0::2], cidx[1::2]
+        px, py = cnx[i1] - cnx[i0], cny[i1] - cny[i0]
+        car = np.hypot(px, py).astype(np.float32)
+        c = [T(np.ascontiguousarray(a)) for a in (cnx, cny, car, (px / car).astype(np.float32), (py / car).astype(np.float32),
+                                                  (-py / car).astype(np.float32), (px / car).astype(np.float32))]
+        ci = T(cidx.astype(np.int32))
+        m = torch.empty((2 * npan, 2 * npan), device=dev)
+        fn = lambda: ctx.panels_on_panels_coeff(o2d.MEM_DEVICE, npan, npan, c[0], c[1], ci, c[2], npan, npan, c[0], c[1], ci,
+                                                c[2], c[3], c[4], c[5], c[6], 1, 1, 2 * npan, m)
     else:
         rng = np.random.default_rng(1)
         qx = T(rng.uniform(-1, 1, n).astype(np.float32)); qy = T(rng.uniform(0.5, 2.5, n).astype(np.float32))
