@@ -712,11 +712,16 @@ def run_ours(args, wl, n1):
         if results == 2:      # every gradient component, same form of the tolerance
             for k in range(2, 6):
                 err = max(err, float(np.abs(gsub[k].astype(np.float64) - ref_out[k]).max() / np.abs(np.asarray(ref_out[k], np.float64)).max()))
+        # the two numbers the reference's nearest thing to a correctness test prints (onbody, extern/onbody/src/
+        # main2dvort.cpp:139-154; u component only): sqrt(max du^2 / mean u^2) and sqrt(sum du^2 / sum u^2)
+        du2 = (gu - np.asarray(ref_out[0], np.float64)) ** 2
+        u2 = np.asarray(ref_out[0], np.float64) ** 2
+        onbody = {"max_error": float(np.sqrt(du2.max() / u2.mean())), "rms_error": float(np.sqrt(du2.sum() / u2.sum()))}
         import oracle
         cpu = {"value": count * sources_per_target(wl, n) / dt, "unit": UNIT, "cores": oracle.host_cores(), "kind": kind,
                "sample": f"{count} strided targets x all {n} sources, one call, OpenMP on all host cores; " + CPU_FLAGS_NOTE
                          + ("; the reference's kernelug_0v_0b in its own loop shape (it ships no velandgrad loop)" if results == 2 else ""),
-               "seconds": dt, "max_rel_err_gpu_vs_cpu": float(err), "tolerance": 1e-5}
+               "seconds": dt, "max_rel_err_gpu_vs_cpu": float(err), "tolerance": 1e-5, "onbody_error_metrics_u": onbody}
         if pan is not None:
             cpu["panels_only"] = panel_parity(ctx, pan["host"], sx[sub], sy[sub])
 
