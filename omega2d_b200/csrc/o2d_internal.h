@@ -93,19 +93,22 @@ inline int res_ncomp(int res) {
 // to any unrolling (RM velocity+gradient 7.23 / 7.22 / 6.98 / 6.84 at 1 / 2 / 8 / 16); velocity + shear rate: R = 4,
 // 16 warps, unroll 4 (RM 9.56, V2 uniform 9.05; the 24-warp R = 2 shape of the first run-walking version 9.37 / 8.59),
 // except EXP and V3, which keep R = 2 / 24 warps / unroll 8 there as well (EXP 7.61 against 7.12, V3 4.58 against 4.38).
+// EXP takes 24 warps x 2 targets for velocity+vorticity and velocity+gradient too (7.17 against 6.76, 5.94 against 5.59;
+// V3: 4.50 / 4.54 and 3.74 / 3.76, unchanged, stays at 16 warps x 3).
 constexpr int pp_targets(int core, int res, bool fine) {
   if (fine) return (res == RES_U || res == RES_VORT) ? 2 : 1;
   switch (res) {
     case RES_U:    return (core == CORE_WL || core == CORE_EXP || core == CORE_V3) ? 4 : 6;
     case RES_VORT: return 4;
     case RES_UE:   return (core == CORE_EXP || core == CORE_V3) ? 2 : O2D_UE_R;
-    case RES_UW:   return O2D_UW_R;
-    default:       return 3;   // RES_UG
+    case RES_UW:   return core == CORE_EXP ? 2 : O2D_UW_R;
+    default:       return core == CORE_EXP ? 2 : 3;   // RES_UG
   }
 }
 constexpr int pp_min_warps(int core, int res, bool fine) {
   if (res == RES_UE) return (core == CORE_EXP || core == CORE_V3) ? 24 : O2D_UE_WARPS;
   if (res == RES_VORT) return 24;
+  if (core == CORE_EXP) return 24;   // every result kind: the far/near votes want resident warps more than registers
   if (res != RES_U) return 16;
   return (fine || core == CORE_EXP || core == CORE_V3) ? 24 : 16;
 }
